@@ -1,0 +1,54 @@
+"""Generates tests/golden/*.npz from the oracle of record: cv2 (OpenCV) -- the library whose
+calcOpticalFlowFarneback / cartToPolar the reference calls (ripcurrents.cpp:215,308).
+
+Run here (container with cv2 4.13.0):   python tests/golden/make_golden.py
+The fixtures are small (<= 160x128) so that they can be committed; the frames are stored too, so the
+tests never depend on the generator being bit-reproducible on another machine.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import cv2  # noqa: E402
+
+from ripcurrents_b200 import synth  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# (name, w, h, params) -- params = (pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags)
+CASES = [
+    ("default_box", 160, 128, (0.5, 2, 3, 2, 15, 1.2, 0)),           # ripcurrents.cpp:215
+    ("gauss_win10", 160, 128, (0.5, 2, 10, 3, 15, 1.2, 256)),        # main.cpp:1119,1481
+    ("gauss_win20", 160, 128, (0.5, 2, 20, 3, 15, 1.2, 256)),        # main.cpp:609,961
+    ("android_box", 160, 128, (0.5, 3, 5, 3, 15, 1.2, 0)),           # RipCurrents_android ripcurrents.cpp:167
+    ("odd_size_box", 131, 97, (0.5, 2, 3, 2, 15, 1.2, 0)),           # ragged size, not a multiple of anything
+    ("poly5_box", 160, 128, (0.5, 3, 15, 3, 5, 1.1, 0)),
+    ("poly7_gauss", 160, 128, (0.5, 4, 21, 3, 7, 1.5, 256)),
+    ("scale08_box", 160, 128, (0.8, 3, 7, 2, 7, 1.5, 0)),            # non power-of-two pyramid
+]
+
+
+def main():
+    cv2.setNumThreads(1)
+    for name, w, h, P in CASES:
+        fr = synth.clip(w, h, 3, seed=3, vx=1.3, vy=-0.7, omega=0.004)
+        flows = [cv2.calcOpticalFlowFarneback(fr[i], fr[i + 1], None, *P) for i in range(2)]
+        np.savez_compressed(os.path.join(HERE, "farneback_%s.npz" % name), frames=np.stack(fr),
+                            flows=np.stack(flows), params=np.array(P, np.float64),
+                            cv2_version=np.array(cv2.__version__))
+    # cartToPolar known answers (degrees), incl. the angle==360 edge and zeros
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.normal(0, 2, 4096), [0, 1, 100, -1, 0, 0, 1e-30, 3, -3],
+                        rng.normal(0, 1e-3, 512)]).astype(np.float32)
+    y = np.concatenate([rng.normal(0, 2, 4096), [0, -1e-7, -1e-6, 0, 1, -1, 1e-30, 3, -3],
+                        rng.normal(0, 1e-3, 512)]).astype(np.float32)
+    mag, ang = cv2.cartToPolar(x, y, angleInDegrees=True)
+    np.savez_compressed(os.path.join(HERE, "cart_to_polar.npz"), x=x, y=y, mag=mag.ravel(), ang=ang.ravel(),
+                        cv2_version=np.array(cv2.__version__))
+
+
+if __name__ == "__main__":
+    main()
