@@ -1,0 +1,180 @@
+/*
+ * ripcurrents_b200.h -- C ABI of the B200-native ripcurrents hot path.
+ *
+ * Drop-in boundary for the per-frame path of borgor/ripcurrents: dense Farneback optical flow,
+ * the temporal aggregation of ripcurrents.cpp (polar conversion, cumulative speed/direction
+ * histograms, tail thresholds, classification, accumulation), the sliding-window flow mean of
+ * main.cpp, and the Euler/bilinear pathline / streakline particle advection.
+ *
+ * The reference has no FFI layer of its own for this path: it calls OpenCV and its own C++ free
+ * functions directly.  Each entry point below names the reference call
+ * (file:line under /root/reference/RipCurrents_main unless stated) that a binding replaces; the
+ * header-compatible C++ wrappers (ripcurrents.hpp / Streakline.hpp / pathlines.h signatures) live in
+ * ripcurrents_b200/cpp and are thin callers of this ABI.  INTEGRATION.md shows the wiring.
+ *
+ * Conventions
+ *   - plain C types only; every function returns RC_OK (0) or a negative RC_ERR_* code and never
+ *     throws; rc_last_error(ctx) gives a message for the last failure on that context.
+ *   - image / flow / seed pointers may be HOST or DEVICE pointers (detected with
+ *     cudaPointerGetAttributes); host buffers are staged through pinned memory on the context's stream.
+ *   - *_step arguments are row strides in BYTES (cv::Mat::step).
+ *   - flow is CV_32FC2: interleaved (dx,dy) fp32, row-major.
+ *   - one rc_ctx per (GPU, camera stream); a context is not thread-safe.
+ *   - all work is enqueued on the context's CUDA stream (rc_set_stream; default: a private
+ *     non-blocking stream).  Calls that return data to HOST memory synchronise that stream; calls whose
+ *     outputs are device pointers do not.
+ *   - there is NO CPU fallback: without a CUDA device rc_create fails with RC_ERR_CUDA.
+ */
+#ifndef RIPCURRENTS_B200_H
+#define RIPCURRENTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RC_OK 0
+#define RC_ERR_INVALID (-1)      /* bad argument */
+#define RC_ERR_CUDA (-2)         /* CUDA runtime error (message in rc_last_error) */
+#define RC_ERR_NOMEM (-3)        /* allocation failed */
+#define RC_ERR_STATE (-4)        /* call order (e.g. no flow computed yet) */
+#define RC_ERR_UNSUPPORTED (-5)  /* parameter outside the supported range */
+
+/* ripcurrents.hpp:7-9 */
+#define RC_HIST_BINS 50
+#define RC_HIST_DIRECTIONS 36
+#define RC_HIST_RESOLUTION 20
+/* hist2d / histsum2d carry one extra row: direction index 36 (angle == 360.0f exactly), which is an
+ * out-of-bounds write in the reference (ripcurrents.cpp:326); it is counted here so totals stay exact. */
+#define RC_HIST_ROWS 37
+
+/* cv::OPTFLOW_FARNEBACK_GAUSSIAN */
+#define RC_FARNEBACK_GAUSSIAN 256
+/* Arithmetic selection (ORed into `flags`; bits unused by OpenCV).
+ * default: fp32 FMA accumulation in the horizontal polynomial-expansion pass, Gaussian tails of the
+ *          expansion kernel below 1e-12 of the centre weight dropped.  Measured within the tolerance of the
+ *          task (mean EPE <= 1e-3 px, max <= 1e-2 px against cv2) with >10x margin, see DESIGN.md.
+ * RC_FARNEBACK_STRICT: every tap, fp64 accumulators exactly where OpenCV uses them, no FMA contraction. */
+#define RC_FARNEBACK_STRICT 0x10000
+
+/* particle-advection variants (the reference's seven copies of the Euler/bilinear step) */
+#define RC_ADV_PATHLINE 0   /* pathlines.cpp:9-46          pt += delta*dt/iterations, no cut-off     */
+#define RC_ADV_LEGACY 1     /* ripcurrents.cpp:656-698     cut-off r > UPPER, pt += delta*dt/iterations */
+#define RC_ADV_MODULE 2     /* ripcurrents_module.cpp:486-528  cut-off r > UPPER, pt += delta*dt     */
+#define RC_ADV_CUT5 3       /* ripcurrents_module.cpp:531-569  streamline_2: cut-off r > 5           */
+#define RC_ADV_FIXED100 4   /* ripcurrents_module.cpp:572-606  streamline_3: 100 steps of delta*0.1  */
+#define RC_ADV_FIELD 5      /* ripcurrents.cpp:611-651 == module:608-648  streamline_field           */
+#define RC_ADV_GET_DELTA 6  /* ripcurrents_module.cpp:650-679  get_delta                             */
+
+typedef struct rc_ctx rc_ctx;
+
+/* ---- library / context ------------------------------------------------------------------------ */
+int rc_version(void);
+const char* rc_error_string(int code);
+const char* rc_last_error(const rc_ctx* ctx);
+/* number of CUDA kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t rc_kernel_launches(const rc_ctx* ctx);
+
+int rc_create(rc_ctx** out, int device);
+void rc_destroy(rc_ctx* ctx);
+int rc_set_stream(rc_ctx* ctx, void* cuda_stream /* cudaStream_t, NULL = private stream */);
+int rc_synchronize(rc_ctx* ctx);
+
+/* ---- A1: dense optical flow ------------------------------------------------------------------- */
+/* Replaces cv::calcOpticalFlowFarneback(prev, next, flow, pyr_scale, levels, winsize, iterations, poly_n,
+ * poly_sigma, flags) as called at ripcurrents.cpp:215, main.cpp:264,609,742,961,1119,1481.
+ * prev/next: 8-bit single-channel w x h.  flow: w x h x 2 fp32 out (may be NULL: result stays on the device,
+ * see rc_flow_device).  OPTFLOW_USE_INITIAL_FLOW (4) is not supported (never used by the reference). */
+int rc_farneback(rc_ctx* ctx, const uint8_t* prev, size_t prev_step, const uint8_t* next, size_t next_step, int w, int h,
+                 float* flow, size_t flow_step, double pyr_scale, int levels, int winsize, int iterations, int poly_n,
+                 double poly_sigma, int flags);
+
+/* Streaming form of the same call for a VideoCapture loop (ripcurrents.cpp:194-217: `u_f1.copyTo(u_f2)`):
+ * rc_flow_configure fixes geometry + parameters; each rc_flow_push consumes ONE new frame, reuses the cached
+ * pyramid + polynomial expansion of the previous frame, and (from the second frame on) produces the flow
+ * previous -> new.  Returns 1 when a flow was produced, 0 for the priming frame, <0 on error. */
+int rc_flow_configure(rc_ctx* ctx, int w, int h, double pyr_scale, int levels, int winsize, int iterations, int poly_n,
+                      double poly_sigma, int flags);
+int rc_flow_push(rc_ctx* ctx, const uint8_t* frame, size_t step, float* flow, size_t flow_step);
+/* device pointer to the most recent flow (w*h*2 fp32, dense rows), valid until the next flow call */
+int rc_flow_device(rc_ctx* ctx, float** dev_flow, int* w, int* h);
+
+/* ---- A2 + A3: polar conversion and cumulative histograms ---------------------------------------- */
+/* Replaces ripcurrents.cpp:305-330 / create_histogram's counting loop (ripcurrents_module.cpp:94-107).
+ * Counters live on the device in the context and are CUMULATIVE (ripcurrents.cpp:147-153) until rc_hist_reset.
+ * flow == NULL means "the context's most recent flow". */
+int rc_hist_reset(rc_ctx* ctx);
+int rc_polar_hist(rc_ctx* ctx, const float* flow, size_t flow_step, int w, int h);
+int rc_hist_get(rc_ctx* ctx, int64_t hist[RC_HIST_BINS], int64_t* histsum,
+                int64_t hist2d[RC_HIST_ROWS * RC_HIST_BINS], int64_t histsum2d[RC_HIST_ROWS]);
+/* adds external counts (e.g. the exclusive prefix of other ranks' frames) */
+int rc_hist_add(rc_ctx* ctx, const int64_t hist2d[RC_HIST_ROWS * RC_HIST_BINS]);
+/* device pointer to the counters: int64[RC_HIST_ROWS*RC_HIST_BINS] hist2d (hist/histsum/histsum2d are its
+ * marginals) -- for NCCL all-gather / all-reduce by the caller */
+int rc_hist_device(rc_ctx* ctx, int64_t** dev_hist2d);
+/* cv::cartToPolar(x, y, mag, angle, true) (ripcurrents.cpp:308) on n points; bit-exact restatement */
+int rc_cart_to_polar(rc_ctx* ctx, const float* flow, size_t n, float* mag, float* angle_deg);
+
+/* ---- A4: thresholds ----------------------------------------------------------------------------- */
+/* Replaces ripcurrents.cpp:333-366 / ripcurrents_module.cpp:110-143, evaluated on the device counters.
+ * Any output pointer may be NULL.  The values also stay on the device for rc_classify_accumulate. */
+int rc_thresholds(rc_ctx* ctx, float* UPPER, float UPPER2d[RC_HIST_DIRECTIONS],
+                  float prop_above_upper[RC_HIST_DIRECTIONS]);
+
+/* ---- A5: classify + accumulate + mask ----------------------------------------------------------- */
+/* Replaces ripcurrents.cpp:376-439 / create_flow + create_accumulationbuffer (module:153-212).
+ * upper: threshold to use; NaN = the value computed by the last rc_thresholds (kept on the device).
+ * The accumulator (.x lane of the reference's CV_32FC3 `accumulator`) lives in the context.
+ * outmask / waveclass / waterclass: w*h u8 outputs, each may be NULL (host or device pointers).
+ *   outmask    255 = calm, 0 = wave                                   (ripcurrents.cpp:436)
+ *   waveclass  0 calm, 1 = val < .2*framecount, 2 = otherwise         (ripcurrents.cpp:429-433)
+ *   waterclass 3 > UPPER, 2 > MID(0.5), 1 > LOWER(0.2), 0 otherwise   (ripcurrents.cpp:384-390) */
+int rc_accumulator_reset(rc_ctx* ctx);
+int rc_classify_accumulate(rc_ctx* ctx, const float* flow, size_t flow_step, int w, int h, float upper, int framecount,
+                           uint8_t* outmask, uint8_t* waveclass, uint8_t* waterclass);
+int rc_accumulator_get(rc_ctx* ctx, float* acc_x /* w*h fp32 */);
+int rc_accumulator_device(rc_ctx* ctx, float** dev_acc_x, int* w, int* h);
+
+/* ---- A6: sliding-window flow mean ---------------------------------------------------------------- */
+/* Replaces main.cpp:1084-1092 + 1143-1153 (W=10), :1446 + 1505-1515 (W=100), module:392-400 (W=300):
+ * avg -= slot/W; slot = flow; avg += slot/W  in fp32, in order.  flow == NULL: the context's last flow. */
+int rc_window_configure(rc_ctx* ctx, int w, int h, int W);
+int rc_window_update(rc_ctx* ctx, const float* flow, size_t flow_step);
+int rc_window_get(rc_ctx* ctx, float* avg, size_t avg_step);
+int rc_window_device(rc_ctx* ctx, float** dev_avg);
+/* subtructAverage (ripcurrents_module.cpp:810-863): flow -= mean(flow); in place; mean_xy[2] out (may be NULL) */
+int rc_subtract_mean(rc_ctx* ctx, float* flow, size_t flow_step, int w, int h, double* mean_xy);
+
+/* ---- A7: particle advection ----------------------------------------------------------------------- */
+/* Replaces streamline / streamline_2 / streamline_3 / streamline_field / get_delta (see RC_ADV_*).
+ * flow == NULL: the context's last flow (w,h ignored).  seeds: n x (x,y) fp32 updated in place.
+ * dist: n fp32 path lengths (RC_ADV_FIELD) or NULL.  home: n x (x,y) int32 home pixels for RC_ADV_FIELD /
+ * RC_ADV_GET_DELTA, NULL = seed i lives at pixel (i % w, i / w) (the reference's per-pixel field). */
+int rc_advect(rc_ctx* ctx, const float* flow, size_t flow_step, int w, int h, float* seeds, size_t n, float dt,
+              int iterations, float upper, int variant, float* dist, const int32_t* home);
+/* One Streakline::runLK frame (Streakline.cpp:22-48) for E emitters, vertex motion taken from the dense flow
+ * (variant RC_ADV_MODULE step, no cut-off).  vertices: E x cap x (x,y), reference order (index 0 = newest);
+ * count[e] vertices valid; after the call count[e] grows by one (until cap). */
+int rc_streakline_step(rc_ctx* ctx, const float* flow, size_t flow_step, int w, int h, const float* emitters, int E,
+                       float* vertices, int32_t* count, int cap, float dt);
+
+/* ---- fused per-frame step (what main()'s loop body does between video.read and imshow) ----------- */
+typedef struct rc_frame_result {
+    int produced;                            /* 1 if a flow was produced (0 for the priming frame) */
+    float UPPER;
+    float UPPER2d[RC_HIST_DIRECTIONS];
+    float prop_above_upper[RC_HIST_DIRECTIONS];
+    int64_t histsum;
+} rc_frame_result;
+/* rc_flow_push + rc_polar_hist + rc_thresholds + rc_classify_accumulate (+ rc_window_update when a window is
+ * configured) for one new frame, on the device, in stream order.  outmask (w*h u8) and result may be NULL;
+ * when both are NULL nothing is copied back and the call does not synchronise. */
+int rc_process_frame(rc_ctx* ctx, const uint8_t* frame, size_t step, int framecount, uint8_t* outmask,
+                     rc_frame_result* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIPCURRENTS_B200_H */

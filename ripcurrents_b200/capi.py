@@ -1,0 +1,290 @@
+"""ctypes binding of the C ABI (include/ripcurrents_b200.h).  Used by the tests and bench.py; the same symbols
+are what a cgo / JNI / C++ binding would call.  There is no CPU fallback: if the shared
+library is missing or no CUDA device is present, construction fails loudly."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "lib", "libripcurrents_b200.so")
+
+HIST_BINS, HIST_DIRECTIONS, HIST_RESOLUTION, HIST_ROWS = 50, 36, 20, 37
+FARNEBACK_GAUSSIAN = 256
+FARNEBACK_STRICT = 0x10000
+ADV_PATHLINE, ADV_LEGACY, ADV_MODULE, ADV_CUT5, ADV_FIXED100, ADV_FIELD, ADV_GET_DELTA = range(7)
+
+# every symbol include/ripcurrents_b200.h declares (tests/test_abi.py checks header <-> library <-> this list)
+SYMBOLS = [
+    "rc_version", "rc_error_string", "rc_last_error", "rc_kernel_launches", "rc_create", "rc_destroy",
+    "rc_set_stream", "rc_synchronize", "rc_farneback", "rc_flow_configure", "rc_flow_push", "rc_flow_device",
+    "rc_hist_reset", "rc_polar_hist", "rc_hist_get", "rc_hist_add", "rc_hist_device", "rc_cart_to_polar",
+    "rc_thresholds", "rc_accumulator_reset", "rc_classify_accumulate", "rc_accumulator_get",
+    "rc_accumulator_device", "rc_window_configure", "rc_window_update", "rc_window_get", "rc_window_device",
+    "rc_subtract_mean", "rc_advect", "rc_streakline_step", "rc_process_frame",
+]
+
+
+class FrameResult(C.Structure):
+    _fields_ = [("produced", C.c_int), ("UPPER", C.c_float), ("UPPER2d", C.c_float * HIST_DIRECTIONS),
+                ("prop_above_upper", C.c_float * HIST_DIRECTIONS), ("histsum", C.c_int64)]
+
+
+class RcError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (no CUDA call is made)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RcError("%s is missing: run `python -m ripcurrents_b200.build` (there is no CPU fallback)" % SO_PATH)
+    lib = C.CDLL(SO_PATH)
+    lib.rc_error_string.restype = C.c_char_p
+    lib.rc_last_error.restype = C.c_char_p
+    lib.rc_last_error.argtypes = [C.c_void_p]
+    lib.rc_kernel_launches.restype = C.c_int64
+    lib.rc_kernel_launches.argtypes = [C.c_void_p]
+    lib.rc_destroy.restype = None
+    lib.rc_destroy.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    """numpy array -> host pointer; int -> raw (device) pointer; None -> NULL; objects with data_ptr() (torch)."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError("unsupported buffer type %r" % type(a))
+
+
+class Context:
+    """One rc_ctx: a (GPU, camera stream) pair."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.rc_create(C.byref(h), C.c_int(device))
+        if rc != 0:
+            raise RcError("rc_create(device=%d) failed: %s (a CUDA device is required; no CPU fallback)"
+                          % (device, self.lib.rc_error_string(rc).decode()))
+        self.h = h
+        self.w = self.h_img = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise RcError("%s: %s" % (self.lib.rc_error_string(rc).decode(), self.lib.rc_last_error(self.h).decode()))
+        return rc
+
+    # -- context -------------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._chk(self.lib.rc_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self._chk(self.lib.rc_synchronize(self.h))
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.rc_kernel_launches(self.h))
+
+    # -- A1 ------------------------------------------------------------------------------------------
+    def farneback(self, prev, nxt, pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags, out=None):
+        prev = np.ascontiguousarray(prev, np.uint8); nxt = np.ascontiguousarray(nxt, np.uint8)
+        h, w = prev.shape
+        assert nxt.shape == prev.shape
+        flow = out if out is not None else np.empty((h, w, 2), np.float32)
+        self._chk(self.lib.rc_farneback(self.h, _ptr(prev), C.c_size_t(prev.strides[0]), _ptr(nxt),
+                                        C.c_size_t(nxt.strides[0]), C.c_int(w), C.c_int(h), _ptr(flow),
+                                        C.c_size_t(w * 8), C.c_double(pyr_scale), C.c_int(levels), C.c_int(winsize),
+                                        C.c_int(iterations), C.c_int(poly_n), C.c_double(poly_sigma), C.c_int(flags)))
+        self.w, self.h_img = w, h
+        return flow
+
+    def flow_configure(self, w, h, pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags):
+        self._chk(self.lib.rc_flow_configure(self.h, C.c_int(w), C.c_int(h), C.c_double(pyr_scale), C.c_int(levels),
+                                             C.c_int(winsize), C.c_int(iterations), C.c_int(poly_n),
+                                             C.c_double(poly_sigma), C.c_int(flags)))
+        self.w, self.h_img = w, h
+
+    def flow_push(self, frame, step=None, flow=None):
+        """frame: numpy u8 (host) / torch tensor / raw device pointer.  Returns 1 when a flow was produced."""
+        if isinstance(frame, np.ndarray):
+            assert frame.dtype == np.uint8 and frame.ndim == 2
+            step = frame.strides[0]
+        return self._chk(self.lib.rc_flow_push(self.h, _ptr(frame), C.c_size_t(step or self.w), _ptr(flow),
+                                               C.c_size_t(self.w * 8)))
+
+    def flow_device(self):
+        p = C.c_void_p(); w = C.c_int(); h = C.c_int()
+        self._chk(self.lib.rc_flow_device(self.h, C.byref(p), C.byref(w), C.byref(h)))
+        return p.value, w.value, h.value
+
+    def flow_host(self):
+        p, w, h = self.flow_device()
+        out = np.empty((h, w, 2), np.float32)
+        _memcpy_d2h(out, p)
+        return out
+
+    # -- A2/A3 ---------------------------------------------------------------------------------------
+    def hist_reset(self):
+        self._chk(self.lib.rc_hist_reset(self.h))
+
+    def polar_hist(self, flow=None, w=0, h=0):
+        if isinstance(flow, np.ndarray):
+            flow = np.ascontiguousarray(flow, np.float32)
+            h, w = flow.shape[:2]
+        self._chk(self.lib.rc_polar_hist(self.h, _ptr(flow), C.c_size_t(w * 8), C.c_int(w), C.c_int(h)))
+
+    def hist_get(self):
+        hist = np.zeros(HIST_BINS, np.int64); histsum = C.c_int64()
+        hist2d = np.zeros((HIST_ROWS, HIST_BINS), np.int64); histsum2d = np.zeros(HIST_ROWS, np.int64)
+        self._chk(self.lib.rc_hist_get(self.h, _ptr(hist), C.byref(histsum), _ptr(hist2d), _ptr(histsum2d)))
+        return hist, int(histsum.value), hist2d, histsum2d
+
+    def hist_add(self, hist2d):
+        hist2d = np.ascontiguousarray(hist2d, np.int64)
+        assert hist2d.size == HIST_ROWS * HIST_BINS
+        self._chk(self.lib.rc_hist_add(self.h, _ptr(hist2d)))
+
+    def hist_device(self):
+        p = C.c_void_p()
+        self._chk(self.lib.rc_hist_device(self.h, C.byref(p)))
+        return p.value
+
+    def cart_to_polar(self, flow):
+        flow = np.ascontiguousarray(flow, np.float32).reshape(-1, 2)
+        n = flow.shape[0]
+        mag = np.empty(n, np.float32); ang = np.empty(n, np.float32)
+        self._chk(self.lib.rc_cart_to_polar(self.h, _ptr(flow), C.c_size_t(n), _ptr(mag), _ptr(ang)))
+        return mag, ang
+
+    # -- A4 ------------------------------------------------------------------------------------------
+    def thresholds(self):
+        up = C.c_float(); up2 = np.zeros(HIST_DIRECTIONS, np.float32); prop = np.zeros(HIST_DIRECTIONS, np.float32)
+        self._chk(self.lib.rc_thresholds(self.h, C.byref(up), _ptr(up2), _ptr(prop)))
+        return float(up.value), up2, prop
+
+    # -- A5 ------------------------------------------------------------------------------------------
+    def accumulator_reset(self):
+        self._chk(self.lib.rc_accumulator_reset(self.h))
+
+    def classify_accumulate(self, flow, upper, framecount, want=("mask", "wave", "water"), w=0, h=0):
+        if isinstance(flow, np.ndarray):
+            flow = np.ascontiguousarray(flow, np.float32)
+            h, w = flow.shape[:2]
+        elif flow is None:
+            w, h = self.w, self.h_img
+        outs = {k: (np.empty((h, w), np.uint8) if k in want else None) for k in ("mask", "wave", "water")}
+        self._chk(self.lib.rc_classify_accumulate(self.h, _ptr(flow), C.c_size_t(w * 8), C.c_int(w), C.c_int(h),
+                                                  C.c_float(upper), C.c_int(framecount), _ptr(outs["mask"]),
+                                                  _ptr(outs["wave"]), _ptr(outs["water"])))
+        return outs["mask"], outs["wave"], outs["water"]
+
+    def accumulator_get(self, w, h):
+        acc = np.empty((h, w), np.float32)
+        self._chk(self.lib.rc_accumulator_get(self.h, _ptr(acc)))
+        return acc
+
+    def accumulator_device(self):
+        p = C.c_void_p(); w = C.c_int(); h = C.c_int()
+        self._chk(self.lib.rc_accumulator_device(self.h, C.byref(p), C.byref(w), C.byref(h)))
+        return p.value, w.value, h.value
+
+    # -- A6 ------------------------------------------------------------------------------------------
+    def window_configure(self, w, h, W):
+        self._chk(self.lib.rc_window_configure(self.h, C.c_int(w), C.c_int(h), C.c_int(W)))
+        self._win = (w, h)
+
+    def window_update(self, flow=None):
+        if isinstance(flow, np.ndarray):
+            flow = np.ascontiguousarray(flow, np.float32)
+        self._chk(self.lib.rc_window_update(self.h, _ptr(flow), C.c_size_t(self._win[0] * 8)))
+
+    def window_get(self):
+        w, h = self._win
+        avg = np.empty((h, w, 2), np.float32)
+        self._chk(self.lib.rc_window_get(self.h, _ptr(avg), C.c_size_t(w * 8)))
+        return avg
+
+    def subtract_mean(self, flow):
+        assert isinstance(flow, np.ndarray) and flow.dtype == np.float32 and flow.flags.c_contiguous
+        h, w = flow.shape[:2]
+        mean = np.zeros(2, np.float64)
+        self._chk(self.lib.rc_subtract_mean(self.h, _ptr(flow), C.c_size_t(w * 8), C.c_int(w), C.c_int(h), _ptr(mean)))
+        return mean
+
+    # -- A7 ------------------------------------------------------------------------------------------
+    def advect(self, flow, seeds, dt, iterations, upper, variant, dist=None, home=None, w=0, h=0, n=None):
+        if isinstance(flow, np.ndarray):
+            flow = np.ascontiguousarray(flow, np.float32)
+            h, w = flow.shape[:2]
+        if isinstance(seeds, np.ndarray):
+            assert seeds.dtype == np.float32 and seeds.flags.c_contiguous
+            n = seeds.size // 2
+        if isinstance(home, np.ndarray):
+            home = np.ascontiguousarray(home, np.int32)
+        self._chk(self.lib.rc_advect(self.h, _ptr(flow), C.c_size_t(w * 8), C.c_int(w), C.c_int(h), _ptr(seeds),
+                                     C.c_size_t(n), C.c_float(dt), C.c_int(iterations), C.c_float(upper),
+                                     C.c_int(variant), _ptr(dist), _ptr(home)))
+
+    def streakline_step(self, flow, emitters, vertices, count, dt=1.0, w=0, h=0, E=None, cap=None):
+        if isinstance(flow, np.ndarray):
+            flow = np.ascontiguousarray(flow, np.float32)
+            h, w = flow.shape[:2]
+        if isinstance(vertices, np.ndarray):
+            E, cap = vertices.shape[:2]
+            assert vertices.dtype == np.float32 and count.dtype == np.int32 and emitters.dtype == np.float32
+        self._chk(self.lib.rc_streakline_step(self.h, _ptr(flow), C.c_size_t(w * 8), C.c_int(w), C.c_int(h),
+                                              _ptr(emitters), C.c_int(E), _ptr(vertices), _ptr(count), C.c_int(cap),
+                                              C.c_float(dt)))
+
+    # -- fused per-frame step ------------------------------------------------------------------------
+    def process_frame(self, frame, framecount, outmask=None, want_result=True, step=None):
+        if isinstance(frame, np.ndarray):
+            step = frame.strides[0]
+        res = FrameResult() if want_result else None
+        rc = self._chk(self.lib.rc_process_frame(self.h, _ptr(frame), C.c_size_t(step or self.w), C.c_int(framecount),
+                                                 _ptr(outmask), C.byref(res) if res is not None else None))
+        return rc, res
+
+
+_cudart = None
+
+
+def _memcpy_d2h(dst, dev_ptr):
+    """Test helper: device -> numpy copy through the CUDA runtime the library was linked with (torch-free)."""
+    global _cudart
+    if _cudart is None:
+        for name in ("libcudart.so.12", "libcudart.so", "/usr/local/cuda/lib64/libcudart.so"):
+            try:
+                _cudart = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if _cudart is None:
+            raise RcError("libcudart not found")
+    rc = _cudart.cudaMemcpy(C.c_void_p(dst.ctypes.data), C.c_void_p(dev_ptr), C.c_size_t(dst.nbytes), C.c_int(2))
+    if rc != 0:
+        raise RcError("cudaMemcpy D2H failed: %d" % rc)

@@ -1,0 +1,56 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads and exports every symbol that
+include/ripcurrents_b200.h declares (no compute calls -- there is no GPU here), and it refuses to run
+without a CUDA device instead of falling back to a CPU path."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "ripcurrents_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rc_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ripcurrents_b200 import build, capi
+    build.build()
+    return capi.load()
+
+
+def test_exports_every_declared_symbol(lib):
+    from ripcurrents_b200 import capi
+    hdr = _header_symbols()
+    assert len(hdr) >= 30
+    assert sorted(capi.SYMBOLS) == hdr, (set(hdr) ^ set(capi.SYMBOLS))
+    for s in hdr:
+        assert hasattr(lib, s), "library does not export %s" % s
+
+
+def test_version_and_error_strings(lib):
+    assert lib.rc_version() >= 100
+    assert lib.rc_error_string(0) == b"ok"
+    assert lib.rc_error_string(-2) == b"CUDA error"
+    assert lib.rc_error_string(-99) == b"unknown error"
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from ripcurrents_b200 import capi
+    with pytest.raises(capi.RcError):
+        capi.Context(0)
+
+
+def test_product_does_not_reference_oracle():
+    # the oracle is test infrastructure: nothing under ripcurrents_b200/ may import, link or call it
+    for dp, _, files in os.walk(os.path.join(ROOT, "ripcurrents_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".hpp", ".cpp", ".cuh")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "rc_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
