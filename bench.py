@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: 1080p Farneback flow + aggregation frame pairs / s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload "C2" (BASELINE.json configs[1]): one 1920x1080 camera stream per GPU, reference default Farneback
+parameters (ripcurrents.cpp:215: pyr_scale 0.5, levels 2 -> 3 pyramid layers, winsize 3, 2 iterations, poly_n 15,
+poly_sigma 1.2, box window), followed per frame by polar conversion + cumulative speed/direction histograms +
+tail thresholds + classify/accumulate/mask (ripcurrents.cpp:305-439) + the 10-frame sliding-window flow mean
+(main.cpp:1143-1153).  A "step" is FRAMES_PER_STEP consecutive new frames of the stream (= that many frame pairs).
+
+  value : pairs/s summed over all ranks, frames already resident in HBM when the timed region starts
+  e2e   : same metric through the C-ABI call with HOST (pinned) frames: per frame one H2D copy of the u8 frame and
+          one D2H read of the outmask + thresholds, inside the timed region
+  roofline : dominant kernel (largest share of device time), algorithmic bytes / CUDA-event duration
+  cpu_baseline / --impl reference : OpenCV's CPU calcOpticalFlowFarneback (cv2, the library the reference calls)
+          + the C port of the reference's aggregation (oracle/), on the box's host cores
+
+Multi-GPU: streams are independent: one stream per rank, no data-path collective in the
+flow; once per step the per-rank accumulators and histograms are all-reduced (NCCL) into a shared wave-activity map.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+PARAMS = (0.5, 2, 3, 2, 15, 1.2, 0)      # ripcurrents.cpp:215
+WINDOW = 10                               # main.cpp:1084
+FRAMES_PER_STEP = 16
+CLIP_FRAMES = 24                          # distinct synthetic frames per rank, cycled
+METRIC = "1080p Farneback flow+aggregation frame pairs/s"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs per worker for the CPU legs (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(n_gpus):
+    return {"workload": "C2: 1920x1080 single stream per GPU, Farneback(0.5,2,3,2,15,1.2,box) -> 3 pyramid layers, "
+                        "+ polar/histogram/thresholds/classify+accumulate + window mean W=10",
+            "frames_per_step": FRAMES_PER_STEP, "streams": n_gpus, "parallelism": "stream-per-GPU x%d" % n_gpus,
+            "l2": "per-step working set (expansion/matrix planes, flow ring) ~0.5 GB per GPU > 126 MB L2; "
+                  "frames cycle through a %d-frame clip" % CLIP_FRAMES}
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def _cpu_worker(args):
+    """One host process: its own clip, `pairs` frame pairs of flow + aggregation.  Returns seconds of work."""
+    seed, pairs, w, h = args
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+    except Exception:
+        cv2 = None
+    from oracle import oracle as O
+    from ripcurrents_b200 import synth
+    fr = synth.clip(w, h, pairs + 1, seed=seed)
+    st = O.HistState()
+    acc = np.zeros(w * h, np.float32)
+    avg = np.zeros(w * h * 2, np.float32)
+    ring = np.zeros((WINDOW, w * h * 2), np.float32)
+    t0 = time.perf_counter()
+    for i in range(pairs):
+        if cv2 is not None:
+            flow = cv2.calcOpticalFlowFarneback(fr[i], fr[i + 1], None, *PARAMS)
+        else:
+            flow = O.farneback(fr[i], fr[i + 1], *PARAMS)
+        O.histogram(flow, st)
+        up, _, _ = O.thresholds(st)
+        O.classify_accumulate(flow, up, 31 + i, acc)
+        O.window_update(avg, ring[i % WINDOW], flow, WINDOW)
+    return time.perf_counter() - t0, cv2 is not None
+
+
+def cpu_leg(pairs_per_worker, workers):
+    """Throughput of the CPU path with `workers` independent processes (OpenCV's Farneback is single-threaded,
+    so frame-pair parallelism is how a host uses its cores).  Returns (pairs/s, cores, kind, sample)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_cpu_worker, [(100 + i, pairs_per_worker, W, H) for i in range(workers)])
+    wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)
+    have_cv2 = all(r[1] for r in res)
+    total = pairs_per_worker * workers
+    kind = "reference" if have_cv2 else "port"
+    what = ("cv2 %s calcOpticalFlowFarneback (OpenCV CPU: the routine ripcurrents.cpp:215 calls)" % _cv2_version()
+            if have_cv2 else "C port oracle/farneback_oracle.c")
+    sample = ("%d pairs of 1080p (%d worker processes x %d pairs), %s + C port of ripcurrents.cpp:305-439 / "
+              "main.cpp:1143-1153 aggregation; timed region %.1f s (clip synthesis excluded, wall %.1f s)"
+              % (total, workers, pairs_per_worker, what, busy, wall))
+    return total / busy, workers, kind, sample
+
+
+def _cv2_version():
+    try:
+        import cv2
+        return cv2.__version__
+    except Exception:
+        return "n/a"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    workers = min(os.cpu_count() or 1, 32)
+    per = args.cpu_pairs or max(2, min(6, args.steps))
+    # W warm-up + K steps: each "step" of this arm is one bounded sample (per worker `per` pairs)
+    vals = []
+    t_all = time.perf_counter()
+    for s in range(args.warmup + args.steps):
+        v, cores, kind, sample = cpu_leg(per, workers)
+        if s >= args.warmup:
+            vals.append(v)
+        if time.perf_counter() - t_all > 240 and len(vals) >= 1:
+            break
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * per * workers / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (+f64 accumulators)",
+            "data": "synthetic moving texture", "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+class DevArr:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"data": (ptr, False), "shape": shape, "typestr": typestr, "version": 2}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from ripcurrents_b200 import Context, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback "
+                         "(use --impl reference for the CPU reference arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # synthetic clip for this rank's camera stream
+    frames = synth.clip(W, H, CLIP_FRAMES, seed=rank)
+    d_frames = [torch.from_numpy(f).to(dev) for f in frames]
+    h_frames = [torch.from_numpy(f).pin_memory() for f in frames]
+    h_mask = torch.empty((H, W), dtype=torch.uint8).pin_memory()
+
+    ctx = Context(local_rank)
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.flow_configure(W, H, *PARAMS)
+    ctx.hist_reset()
+    ctx.window_configure(W, H, WINDOW)
+
+    state = {"fc": 0}
+    shared = {}
+
+    def setup_shared():
+        # shared (all-camera) accumulators for the per-step all-reduce
+        if world > 1 and not shared:
+            p, aw, ah = ctx.accumulator_device()
+            shared["acc"] = torch.as_tensor(DevArr(p, (ah, aw), "<f4"), device=dev)
+            shared["hist"] = torch.as_tensor(DevArr(ctx.hist_device(), (37 * 50,), "<i8"), device=dev)
+            shared["acc_all"] = torch.empty_like(shared["acc"])
+            shared["hist_all"] = torch.empty_like(shared["hist"])
+
+    def step_device():
+        for _ in range(FRAMES_PER_STEP):
+            fc = state["fc"]
+            ctx.process_frame(d_frames[fc % CLIP_FRAMES].data_ptr(), fc, None, want_result=False, step=W)
+            state["fc"] = fc + 1
+        if world > 1:
+            setup_shared()
+            shared["acc_all"].copy_(shared["acc"]); shared["hist_all"].copy_(shared["hist"])
+            dist.all_reduce(shared["acc_all"]); dist.all_reduce(shared["hist_all"])
+
+    last = {}
+
+    def step_e2e():
+        for _ in range(FRAMES_PER_STEP):
+            fc = state["fc"]
+            rc, res = ctx.process_frame(h_frames[fc % CLIP_FRAMES].data_ptr(), fc, h_mask.data_ptr(), want_result=True,
+                                        step=W)
+            last["upper"] = res.UPPER
+            state["fc"] = fc + 1
+        if world > 1:
+            setup_shared()
+            shared["acc_all"].copy_(shared["acc"]); shared["hist_all"].copy_(shared["hist"])
+            dist.all_reduce(shared["acc_all"]); dist.all_reduce(shared["hist_all"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        l0 = ctx.kernel_launches
+        e0.record(stream)
+        for _ in range(steps):
+            step_fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ctx.kernel_launches - l0
+
+    # prime (first frame produces no flow) so that every timed frame is a full pair
+    ctx.process_frame(d_frames[0].data_ptr(), 0, None, want_result=False, step=W)
+    state["fc"] = 1
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, launches = timed(step_device, args.steps, max(args.warmup, 3))
+    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+
+    pairs = FRAMES_PER_STEP * args.steps * world
+    value = pairs / (ms_dev * 1e-3)
+    e2e_value = pairs / (ms_e2e * 1e-3)
+
+    # per-kernel device time (CUDA events around every launch, same steps, separate pass so that the event
+    # overhead does not perturb `value`)
+    ctx.profile_reset(); ctx.profile_enable(True)
+    for _ in range(min(args.steps, 5)):
+        step_device()
+    torch.cuda.synchronize(dev)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    kernels = {}
+    total_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    for name, v in prof.items():
+        gbs = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0
+        kernels[name] = {"share": round(v["ms"] / total_ms, 4), "avg_us": round(1e3 * v["ms"] / v["launches"], 2),
+                         "launches": v["launches"], "alg_GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])[0] if prof else None
+    roofline = None
+    if dom:
+        v = prof[dom]
+        achieved = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "alg_bytes_per_launch": v["bytes"] / v["launches"], "avg_launch_us": 1e3 * v["ms"] / v["launches"],
+                    "share_of_step": round(v["ms"] / total_ms, 4)}
+        tfile = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu capture
+        try:
+            roofline["traffic"] = json.load(open(tfile)).get(dom)
+        except Exception:
+            pass
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (+f64 accumulators)",
+                "data": "synthetic moving texture (ripcurrents_b200/synth.py), %d-frame clip per stream" % CLIP_FRAMES,
+                "config": config_dict(world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": FRAMES_PER_STEP * W * H,
+                        "d2h_bytes_per_step": FRAMES_PER_STEP * (W * H + 320), "ms_per_step": ms_e2e / args.steps,
+                        "api": "rc_process_frame(host frame) -> outmask + thresholds on the host"},
+                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "kernels": kernels,
+                "check": {"last_UPPER": last.get("upper")}}
+        if world == 1 and not args.no_cpu_baseline:
+            workers = min(os.cpu_count() or 1, 32)
+            v, cores, kind, sample = cpu_leg(args.cpu_pairs or 2, workers)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)]
+        cmd += sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -82,6 +82,14 @@ void rc_destroy(rc_ctx* ctx);
 int rc_set_stream(rc_ctx* ctx, void* cuda_stream /* cudaStream_t, NULL = private stream */);
 int rc_synchronize(rc_ctx* ctx);
 
+/* Per-kernel device timing for bench.py's roofline: when enabled every kernel launch is bracketed by two CUDA
+ * events on the launching stream; rc_profile_get returns, per kernel class, the summed duration, the number of
+ * launches and the summed ALGORITHMIC bytes (DESIGN.md lists the per-pixel figures).  Off by default. */
+int rc_profile_enable(rc_ctx* ctx, int on);
+int rc_profile_reset(rc_ctx* ctx);
+int rc_profile_count(void);
+int rc_profile_get(rc_ctx* ctx, int idx, const char** name, double* total_ms, int64_t* launches, double* alg_bytes);
+
 /* ---- A1: dense optical flow ------------------------------------------------------------------- */
 /* Replaces cv::calcOpticalFlowFarneback(prev, next, flow, pyr_scale, levels, winsize, iterations, poly_n,
  * poly_sigma, flags) as called at ripcurrents.cpp:215, main.cpp:264,609,742,961,1119,1481.

@@ -17,7 +17,8 @@ ADV_PATHLINE, ADV_LEGACY, ADV_MODULE, ADV_CUT5, ADV_FIXED100, ADV_FIELD, ADV_GET
 # every symbol include/ripcurrents_b200.h declares (tests/test_abi.py checks header <-> library <-> this list)
 SYMBOLS = [
     "rc_version", "rc_error_string", "rc_last_error", "rc_kernel_launches", "rc_create", "rc_destroy",
-    "rc_set_stream", "rc_synchronize", "rc_farneback", "rc_flow_configure", "rc_flow_push", "rc_flow_device",
+    "rc_set_stream", "rc_synchronize", "rc_profile_enable", "rc_profile_reset", "rc_profile_count", "rc_profile_get",
+    "rc_farneback", "rc_flow_configure", "rc_flow_push", "rc_flow_device",
     "rc_hist_reset", "rc_polar_hist", "rc_hist_get", "rc_hist_add", "rc_hist_device", "rc_cart_to_polar",
     "rc_thresholds", "rc_accumulator_reset", "rc_classify_accumulate", "rc_accumulator_get",
     "rc_accumulator_device", "rc_window_configure", "rc_window_update", "rc_window_get", "rc_window_device",
@@ -108,6 +109,22 @@ class Context:
     @property
     def kernel_launches(self):
         return int(self.lib.rc_kernel_launches(self.h))
+
+    def profile_enable(self, on=True):
+        self._chk(self.lib.rc_profile_enable(self.h, C.c_int(1 if on else 0)))
+
+    def profile_reset(self):
+        self._chk(self.lib.rc_profile_reset(self.h))
+
+    def profile_read(self):
+        """-> {kernel class: dict(ms=total ms, launches=n, bytes=total algorithmic bytes)} for classes that ran"""
+        out = {}
+        for i in range(self.lib.rc_profile_count()):
+            name = C.c_char_p(); ms = C.c_double(); n = C.c_int64(); b = C.c_double()
+            self._chk(self.lib.rc_profile_get(self.h, C.c_int(i), C.byref(name), C.byref(ms), C.byref(n), C.byref(b)))
+            if n.value:
+                out[name.value.decode()] = dict(ms=ms.value, launches=int(n.value), bytes=b.value)
+        return out
 
     # -- A1 ------------------------------------------------------------------------------------------
     def farneback(self, prev, nxt, pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags, out=None):

@@ -120,9 +120,9 @@ void rc_launch_advect(rc_ctx* c, const float* flow, size_t flow_step, int w, int
 {
     if (!n) return;
     FlowView F{reinterpret_cast<const char*>(flow), flow_step, w, h};
+    KScope ks(c, K_ADVECT, (16.0 + (dist ? 8.0 : 0.0)) * n + 8.0 * w * h);
     advect_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(F, seeds, n, dt, iterations, upper, variant, dist,
                                                                      home);
-    c->launches++;
 }
 
 // vertices is updated out of place into `vout` by the caller-provided scratch; the launcher copies back.
@@ -135,8 +135,8 @@ void rc_launch_streakline(rc_ctx* c, const float* flow, size_t flow_step, int w,
     float* vout = reinterpret_cast<float*>(c->d_tmp2);   // sized by the API layer
     int gx = (cap + 255) / 256; if (gx > 64) gx = 64;
     dim3 g(gx, E);
+    KScope ks(c, K_STREAKLINE, 16.0 * E * cap + 8.0 * w * h, 2);
     streakline_kernel<<<g, 256, 0, c->stream>>>(F, emitters, E, vertices, vout, count, cap, dt, w * 0.1, h * 0.1);
     streakline_count_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(count, E, cap);
     cudaMemcpyAsync(vertices, vout, bytes, cudaMemcpyDeviceToDevice, c->stream);
-    c->launches += 2;
 }

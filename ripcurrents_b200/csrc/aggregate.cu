@@ -222,21 +222,21 @@ int grid_for(size_t n, int block, int per_sm)
 void rc_launch_polar_hist(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, unsigned long long* hist2d)
 {
     const size_t n = (size_t)w * h;
+    KScope ks(c, K_POLAR_HIST, 8.0 * n);
     polar_hist_kernel<<<grid_for(n, 256, 4), 256, 0, c->stream>>>(flow, flow_step, w, h, hist2d);
-    c->launches++;
 }
 
 void rc_launch_cart_to_polar(rc_ctx* c, const float* flow, size_t n, float* mag, float* ang)
 {
     if (!n) return;
+    KScope ks(c, K_MISC, 16.0 * n);
     cart_to_polar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(flow, n, mag, ang);
-    c->launches++;
 }
 
 void rc_launch_thresholds(rc_ctx* c, const unsigned long long* hist2d, float* thr)
 {
+    KScope ks(c, K_THRESHOLDS, 8.0 * RC_HIST_ROWS * RC_HIST_BINS);
     thresholds_kernel<<<1, 64, 0, c->stream>>>(hist2d, thr);
-    c->launches++;
 }
 
 void rc_launch_classify(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float upper, const float* thr,
@@ -245,24 +245,24 @@ void rc_launch_classify(rc_ctx* c, const float* flow, size_t flow_step, int w, i
 {
     const size_t n = (size_t)w * h;
     const float inv = W > 0 ? (float)(1.0 / (double)W) : 0.f;
+    KScope ks(c, K_CLASSIFY, (8.0 + 8.0 + (mask ? 1.0 : 0.0) + (avg ? 32.0 : 0.0)) * n);
     classify_kernel<<<grid_for(n, 256, 8), 256, 0, c->stream>>>(flow, flow_step, w, h, upper, thr, framecount, acc, mask,
                                                                waveclass, waterclass, ring_slot, avg, inv);
-    c->launches++;
 }
 
 void rc_launch_window_update(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float* slot, float* avg, int W)
 {
     const size_t n = (size_t)w * h;
+    KScope ks(c, K_WINDOW, 40.0 * n);
     window_update_kernel<<<grid_for(n, 256, 8), 256, 0, c->stream>>>(flow, flow_step, w, h, slot, avg,
                                                                     (float)(1.0 / (double)W));
-    c->launches++;
 }
 
 void rc_launch_subtract_mean(rc_ctx* c, float* flow, size_t flow_step, int w, int h, double* d_sums)
 {
     const size_t n = (size_t)w * h;
     cudaMemsetAsync(d_sums, 0, 2 * sizeof(double), c->stream);
+    KScope ks(c, K_MISC, 24.0 * n, 2);
     sum_flow_kernel<<<grid_for(n, 256, 4), 256, 0, c->stream>>>(flow, flow_step, w, h, d_sums);
     sub_mean_kernel<<<grid_for(n, 256, 8), 256, 0, c->stream>>>(flow, flow_step, w, h, d_sums);
-    c->launches += 2;
 }

@@ -9,6 +9,10 @@
 
 #define RC_VERSION 100
 
+const char* const rc_kernel_names[K_COUNT] = {"pyr_h", "pyr_v", "polyexp", "update_matrices", "flow_iter_fused",
+                                              "flow_iter_final", "polar_hist", "thresholds", "classify", "window_mean",
+                                              "advect", "streakline", "misc"};
+
 namespace {
 
 int fail(rc_ctx* c, int code, const char* fmt, const char* detail = "")
@@ -193,6 +197,21 @@ int copy_out(rc_ctx* c, void* dst, size_t dst_step, const void* d_src, size_t sr
 
 }  // namespace
 
+static void prof_drain(rc_ctx* c)
+{
+    if (c->prof.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& r : c->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            c->prof_ms[r.id] += ms; c->prof_bytes[r.id] += r.bytes; c->prof_n[r.id] += 1;
+        } else cudaGetLastError();
+        c->ev_pool.push_back(r.a); c->ev_pool.push_back(r.b);
+    }
+    c->prof.clear();
+}
+
+
 // =====================================================================================================
 extern "C" {
 
@@ -243,6 +262,8 @@ void rc_destroy(rc_ctx* c)
                     c->d_avg};
     for (void* p : bufs) if (p) cudaFree(p);
     if (c->h_pin) cudaFreeHost(c->h_pin);
+    prof_drain(c);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -266,6 +287,39 @@ int rc_synchronize(rc_ctx* c)
 {
     if (!c) return RC_ERR_INVALID;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return RC_OK;
+}
+
+// ---- per-kernel device timing ----------------------------------------------------------------------------
+int rc_profile_enable(rc_ctx* c, int on)
+{
+    if (!c) return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    prof_drain(c);
+    c->prof_on = on != 0;
+    return RC_OK;
+}
+
+int rc_profile_reset(rc_ctx* c)
+{
+    if (!c) return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    prof_drain(c);
+    for (int i = 0; i < K_COUNT; i++) { c->prof_ms[i] = 0; c->prof_bytes[i] = 0; c->prof_n[i] = 0; }
+    return RC_OK;
+}
+
+int rc_profile_count(void) { return K_COUNT; }
+
+int rc_profile_get(rc_ctx* c, int idx, const char** name, double* total_ms, int64_t* launches, double* alg_bytes)
+{
+    if (!c || idx < 0 || idx >= K_COUNT) return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    prof_drain(c);
+    if (name) *name = rc_kernel_names[idx];
+    if (total_ms) *total_ms = c->prof_ms[idx];
+    if (launches) *launches = c->prof_n[idx];
+    if (alg_bytes) *alg_bytes = c->prof_bytes[idx];
     return RC_OK;
 }
 

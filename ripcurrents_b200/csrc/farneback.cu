@@ -316,11 +316,16 @@ void rc_launch_pyr_layer(rc_ctx* c, const uint8_t* d_img, size_t step, int W, in
     const double sx = 1.0 / ((double)L.w / (double)W), sy = 1.0 / ((double)L.h / (double)H);
     dim3 b(32, 8);
     dim3 g1((L.w + 31) / 32, (H + 7) / 8);
-    pyr_h_kernel<<<g1, b, 0, c->stream>>>(d_img, step, W, H, L.w, sx, two, L.smooth, L.htmp);
+    {
+        KScope ks(c, K_PYR_H, (double)W * H);
+        pyr_h_kernel<<<g1, b, 0, c->stream>>>(d_img, step, W, H, L.w, sx, two, L.smooth, L.htmp);
+    }
     dim3 g2((L.w + 31) / 32, (L.h + 7) / 8);
     const int pitch = (L.w + 31) / 32 * 32;
-    pyr_v_kernel<<<g2, b, 0, c->stream>>>(L.htmp, W, H, L.w, L.h, sx, sy, two, L.smooth, L.I, pitch);
-    c->launches += 2;
+    {
+        KScope ks(c, K_PYR_V, 4.0 * L.w * L.h);
+        pyr_v_kernel<<<g2, b, 0, c->stream>>>(L.htmp, W, H, L.w, L.h, sx, sy, two, L.smooth, L.I, pitch);
+    }
 }
 
 void rc_launch_polyexp(rc_ctx* c, const float* I, int w, int h, int pitch, const Planes& R)
@@ -334,8 +339,8 @@ void rc_launch_polyexp(rc_ctx* c, const float* I, int w, int h, int pitch, const
         configured = smem;
     }
     dim3 g((w + TX - 1) / TX, (h + TY - 1) / TY);
+    KScope ks(c, K_POLYEXP, 24.0 * w * h);
     polyexp_ref_kernel<TX, TY><<<g, 256, smem, c->stream>>>(I, w, h, pitch, R, c->poly);
-    c->launches += 1;
 }
 
 void rc_launch_update_matrices(rc_ctx* c, const Planes& R0, const Planes& R1, const Planes& M, int flow_mode,
@@ -344,8 +349,8 @@ void rc_launch_update_matrices(rc_ctx* c, const Planes& R0, const Planes& R1, co
     dim3 b(32, 8), g((R0.w + 31) / 32, (R0.h + 7) / 8);
     double sx = 1.0, sy = 1.0;
     if (flow_mode == 1) { sx = 1.0 / ((double)R0.w / (double)cw); sy = 1.0 / ((double)R0.h / (double)ch); }
+    KScope ks(c, K_UPDATE_MATRICES, (flow_mode ? 62.0 : 60.0) * R0.w * R0.h);
     update_matrices_kernel<<<g, b, 0, c->stream>>>(R0, R1, M, flow_mode, flow, cw, ch, sx, sy, flow_scale);
-    c->launches += 1;
 }
 
 void rc_launch_update_flow(rc_ctx* c, const Planes& M_in, const Planes& R0, const Planes& R1, const Planes& M_out,
@@ -354,6 +359,7 @@ void rc_launch_update_flow(rc_ctx* c, const Planes& M_in, const Planes& R0, cons
     (void)hist2d;
     dim3 b(32, 8), g((M_in.w + 31) / 32, (M_in.h + 7) / 8);
     const bool fuse = M_out.p != nullptr;
+    KScope ks(c, fuse ? K_FLOW_ITER_FUSED : K_FLOW_ITER_FINAL, (fuse ? 80.0 : 28.0) * M_in.w * M_in.h);
     if (c->prm.flags & RC_FARNEBACK_GAUSSIAN) {
         if (fuse) update_flow_gauss_ref_kernel<true><<<g, b, 0, c->stream>>>(M_in, c->gwin, R0, R1, M_out, flow_out);
         else update_flow_gauss_ref_kernel<false><<<g, b, 0, c->stream>>>(M_in, c->gwin, R0, R1, M_out, flow_out);
@@ -363,5 +369,4 @@ void rc_launch_update_flow(rc_ctx* c, const Planes& M_in, const Planes& R0, cons
         if (fuse) update_flow_box_ref_kernel<true><<<g, b, 0, c->stream>>>(M_in, m, scale, R0, R1, M_out, flow_out);
         else update_flow_box_ref_kernel<false><<<g, b, 0, c->stream>>>(M_in, m, scale, R0, R1, M_out, flow_out);
     }
-    c->launches += 1;
 }

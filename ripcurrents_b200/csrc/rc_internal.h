@@ -60,8 +60,21 @@ struct Layer {
     float* flow = nullptr;         // w*h*2 fp32 (dense) flow of this layer
 };
 
+// kernel classes for rc_profile_* (per-launch CUDA-event timing) -- order matches rc_kernel_names[]
+enum RcKernelId { K_PYR_H = 0, K_PYR_V, K_POLYEXP, K_UPDATE_MATRICES, K_FLOW_ITER_FUSED, K_FLOW_ITER_FINAL,
+                  K_POLAR_HIST, K_THRESHOLDS, K_CLASSIFY, K_WINDOW, K_ADVECT, K_STREAKLINE, K_MISC, K_COUNT };
+extern const char* const rc_kernel_names[K_COUNT];
+
+struct ProfRec { int id; cudaEvent_t a, b; double bytes; };
+
 struct rc_ctx {
     int device = 0;
+    bool prof_on = false;
+    std::vector<ProfRec> prof;          // pending records (events not yet read)
+    std::vector<cudaEvent_t> ev_pool;   // recycled events
+    double prof_ms[K_COUNT] = {0};
+    double prof_bytes[K_COUNT] = {0};
+    int64_t prof_n[K_COUNT] = {0};
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
@@ -104,6 +117,28 @@ struct rc_ctx {
     float* d_avg = nullptr;
 
     // advection scratch handled through d_tmp
+};
+
+// RAII bracket around one kernel launch: counts it and, when profiling is on, times it with two CUDA events on
+// the launching stream.  `bytes` = ALGORITHMIC bytes of this launch ("Kernels and their rooflines").
+struct KScope {
+    rc_ctx* c; int id; double bytes; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(rc_ctx* c)
+    {
+        cudaEvent_t e;
+        if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    KScope(rc_ctx* c_, int id_, double bytes_, int nlaunch = 1) : c(c_), id(id_), bytes(bytes_)
+    {
+        c->launches += nlaunch;
+        if (c->prof_on) { a = get(c); b = get(c); cudaEventRecord(a, c->stream); }
+    }
+    ~KScope()
+    {
+        if (a) { cudaEventRecord(b, c->stream); c->prof.push_back(ProfRec{id, a, b, bytes}); }
+    }
 };
 
 // ---- kernel launchers (farneback.cu) -------------------------------------------------------------

@@ -52,7 +52,7 @@ def test_histogram_thresholds_exact(ctx, oracle, shape):
         hist, histsum, hist2d, histsum2d = ctx.hist_get()
         assert np.array_equal(hist, st.hist) and histsum == int(st.histsum[0])
         assert np.array_equal(hist2d, st.hist2d) and np.array_equal(histsum2d, st.histsum2d)
-        assert hist2d[36].sum() == f + 1
+        assert hist2d[36].sum() >= f + 1      # the planted (1,-1e-7) pixel; random data adds a few more
         up, up2, prop = ctx.thresholds()
         rup, rup2, rprop = oracle.thresholds(st)
         assert up == rup and np.array_equal(up2, rup2) and np.array_equal(prop, rprop, equal_nan=True)
