@@ -37,8 +37,9 @@ if ROOT not in sys.path:
 W, H = 1920, 1080
 PARAMS = (0.5, 2, 3, 2, 15, 1.2, 0)      # ripcurrents.cpp:215
 WINDOW = 10                               # main.cpp:1084
-FRAMES_PER_STEP = 16
-CLIP_FRAMES = 24                          # distinct synthetic frames per rank, cycled
+FRAMES_PER_STEP = 16                      # = the context's max_batch: one batched launch sequence per step
+CLIP_FRAMES = 17                          # distinct synthetic frames per rank; played 0..16,15..1 (ping-pong, period
+                                          # 32 = two steps) so that consecutive frames always differ by one motion step
 METRIC = "1080p Farneback flow+aggregation frame pairs/s"
 UNIT = "pairs/s"
 
@@ -198,18 +199,26 @@ def run_ours(args, rank, world, local_rank):
 
     # synthetic clip for this rank's camera stream
     frames = synth.clip(W, H, CLIP_FRAMES, seed=rank)
-    d_frames = [torch.from_numpy(f).to(dev) for f in frames]
-    h_frames = [torch.from_numpy(f).pin_memory() for f in frames]
-    h_mask = torch.empty((H, W), dtype=torch.uint8).pin_memory()
+    order = list(range(CLIP_FRAMES)) + list(range(CLIP_FRAMES - 2, 0, -1))          # 32 frames = 2 steps
+    assert len(order) == 2 * FRAMES_PER_STEP
+    seq = np.stack([frames[i] for i in order])
+    h_seq = torch.from_numpy(seq).pin_memory()                                       # [32, H, W] u8, pinned host
+    d_seq = h_seq.to(dev)                                                            # same, resident in HBM
+    h_masks = [torch.empty((FRAMES_PER_STEP, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    from ripcurrents_b200 import capi
+    h_results = [(capi.FrameResult * FRAMES_PER_STEP)() for _ in range(2)]
+    NB = W * H * FRAMES_PER_STEP
 
     ctx = Context(local_rank)
-    stream = torch.cuda.current_stream(dev)
+    # all work of this rank (kernels, NCCL, timing events) goes to ONE explicit stream
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
-    ctx.flow_configure(W, H, *PARAMS)
+    ctx.flow_configure_batch(W, H, *PARAMS, FRAMES_PER_STEP)
     ctx.hist_reset()
     ctx.window_configure(W, H, WINDOW)
 
-    state = {"fc": 0}
     shared = {}
 
     def setup_shared():
@@ -222,10 +231,10 @@ def run_ours(args, rank, world, local_rank):
             shared["hist_all"] = torch.empty_like(shared["hist"])
 
     def step_device():
-        for _ in range(FRAMES_PER_STEP):
-            fc = state["fc"]
-            ctx.process_frame(d_frames[fc % CLIP_FRAMES].data_ptr(), fc, None, want_result=False, step=W)
-            state["fc"] = fc + 1
+        s = state["step"]
+        ctx.process_frames(d_seq.data_ptr() + (s & 1) * NB, 31 + s * FRAMES_PER_STEP, None, want_results=False,
+                           count=FRAMES_PER_STEP)
+        state["step"] = s + 1
         if world > 1:
             setup_shared()
             shared["acc_all"].copy_(shared["acc"]); shared["hist_all"].copy_(shared["hist"])
@@ -234,12 +243,12 @@ def run_ours(args, rank, world, local_rank):
     last = {}
 
     def step_e2e():
-        for _ in range(FRAMES_PER_STEP):
-            fc = state["fc"]
-            rc, res = ctx.process_frame(h_frames[fc % CLIP_FRAMES].data_ptr(), fc, h_mask.data_ptr(), want_result=True,
-                                        step=W)
-            last["upper"] = res.UPPER
-            state["fc"] = fc + 1
+        # public API with HOST buffers: pinned frames in, per-frame masks + threshold records out; the submit is
+        # asynchronous (copies of step s+1 / s-1 overlap the kernels of step s), results are complete after wait()
+        s = state["step"]
+        ctx.process_frames(h_seq.data_ptr() + (s & 1) * NB, 31 + s * FRAMES_PER_STEP, h_masks[s & 1].data_ptr(),
+                           count=FRAMES_PER_STEP, submit_only=True, results=h_results[s & 1])
+        state["step"] = s + 1
         if world > 1:
             setup_shared()
             shared["acc_all"].copy_(shared["acc"]); shared["hist_all"].copy_(shared["hist"])
@@ -253,12 +262,14 @@ def run_ours(args, rank, world, local_rank):
     def timed(step_fn, steps, warmup):
         for _ in range(warmup):
             step_fn()
+        ctx.wait()
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         l0 = ctx.kernel_launches
         e0.record(stream)
         for _ in range(steps):
             step_fn()
+        ctx.wait()                 # all device->host copies of the region have landed (no-op for the device leg)
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -268,14 +279,14 @@ def run_ours(args, rank, world, local_rank):
             ms = float(t.item())
         return ms, ctx.kernel_launches - l0
 
-    # prime (first frame produces no flow) so that every timed frame is a full pair
-    ctx.process_frame(d_frames[0].data_ptr(), 0, None, want_result=False, step=W)
-    state["fc"] = 1
+    # prime (the very first frame produces no flow) so that every timed frame completes a pair
+    state = {"step": 0}
+    step_device(); step_device()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_dev, launches = timed(step_device, args.steps, max(args.warmup, 3))
-    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    ms_e2e, _ = timed(step_e2e, args.steps, 2)
     sampler.stop_flag = True
     sampler.join(timeout=3)
 
@@ -328,9 +339,10 @@ def run_ours(args, rank, world, local_rank):
                 "config": config_dict(world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": FRAMES_PER_STEP * W * H,
                         "d2h_bytes_per_step": FRAMES_PER_STEP * (W * H + 320), "ms_per_step": ms_e2e / args.steps,
-                        "api": "rc_process_frame(host frame) -> outmask + thresholds on the host"},
+                        "api": "rc_submit_frames(16 pinned host frames) -> 16 outmasks + threshold records on the host, rc_wait"},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "kernels": kernels,
-                "check": {"last_UPPER": last.get("upper")}}
+                "check": {"last_UPPER": float(h_results[(state["step"] - 1) & 1][FRAMES_PER_STEP - 1].UPPER),
+                          "histsum": int(h_results[(state["step"] - 1) & 1][FRAMES_PER_STEP - 1].histsum)}}
         if world == 1 and not args.no_cpu_baseline:
             workers = min(os.cpu_count() or 1, 32)
             v, cores, kind, sample = cpu_leg(args.cpu_pairs or 2, workers)

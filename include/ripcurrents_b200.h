@@ -79,7 +79,9 @@ int64_t rc_kernel_launches(const rc_ctx* ctx);
 
 int rc_create(rc_ctx** out, int device);
 void rc_destroy(rc_ctx* ctx);
-int rc_set_stream(rc_ctx* ctx, void* cuda_stream /* cudaStream_t, NULL = private stream */);
+/* cuda_stream: a cudaStream_t.  NULL selects a private non-blocking stream (the default); to run on the legacy
+ * default stream pass cudaStreamLegacy ((void*)1), for the per-thread default stream cudaStreamPerThread ((void*)2). */
+int rc_set_stream(rc_ctx* ctx, void* cuda_stream);
 int rc_synchronize(rc_ctx* ctx);
 
 /* Per-kernel device timing for bench.py's roofline: when enabled every kernel launch is bracketed by two CUDA
@@ -108,6 +110,20 @@ int rc_flow_configure(rc_ctx* ctx, int w, int h, double pyr_scale, int levels, i
 int rc_flow_push(rc_ctx* ctx, const uint8_t* frame, size_t step, float* flow, size_t flow_step);
 /* device pointer to the most recent flow (w*h*2 fp32, dense rows), valid until the next flow call */
 int rc_flow_device(rc_ctx* ctx, float** dev_flow, int* w, int* h);
+
+/* Batched streaming form -- the B200-native way to run a recorded clip: up to max_batch consecutive frames go
+ * through every kernel together (one launch per stage for the whole batch), which is what keeps 148 SMs busy on
+ * the small pyramid layers.  Frame j of the call starts at frames + j*frame_stride.  flows (may be NULL) receives
+ * the produced flows back to back (flow_stride bytes apart).  Returns the number of flows produced: count, or
+ * count-1 when the first frame of the call primed an empty context.  Device-pointer input may exceed max_batch
+ * (it is processed in sub-batches); host input is limited to max_batch frames per call. */
+int rc_flow_configure_batch(rc_ctx* ctx, int w, int h, double pyr_scale, int levels, int winsize, int iterations,
+                            int poly_n, double poly_sigma, int flags, int max_batch);
+int rc_flow_push_batch(rc_ctx* ctx, const uint8_t* frames, size_t step, size_t frame_stride, int count, float* flows,
+                       size_t flow_step, size_t flow_stride);
+/* device pointer to the flow produced `back` pairs before the most recent one (0 = most recent); flows stay
+ * resident for max_batch + window pairs */
+int rc_flow_device_at(rc_ctx* ctx, int back, float** dev_flow);
 
 /* ---- A2 + A3: polar conversion and cumulative histograms ---------------------------------------- */
 /* Replaces ripcurrents.cpp:305-330 / create_histogram's counting loop (ripcurrents_module.cpp:94-107).
@@ -181,6 +197,20 @@ typedef struct rc_frame_result {
  * when both are NULL nothing is copied back and the call does not synchronise. */
 int rc_process_frame(rc_ctx* ctx, const uint8_t* frame, size_t step, int framecount, uint8_t* outmask,
                      rc_frame_result* result);
+/* The same for `count` (<= max_batch) consecutive frames: frame i of the call has loop counter framecount0 + i.
+ * outmasks: count masks mask_stride bytes apart (entries of frames that produced no flow are left untouched);
+ * results: count records.  Temporal state (cumulative histograms -> per-frame thresholds, accumulator, window
+ * mean) advances frame by frame in the reference's order inside the batch. */
+int rc_process_frames(rc_ctx* ctx, const uint8_t* frames, size_t step, size_t frame_stride, int count, int framecount0,
+                      uint8_t* outmasks, size_t mask_stride, rc_frame_result* results);
+/* Asynchronous form for PINNED host buffers: returns as soon as the work is enqueued.  Host->device copies run on
+ * a copy stream into one of two staging slots, kernels on the context stream, device->host copies on a third
+ * stream, so the transfers of batch s+1 / s-1 overlap the kernels of batch s.  Frames, outmasks and results of a
+ * submit must stay untouched until rc_wait() -- or until the second-next rc_submit_frames returns, which waits for
+ * the batch that used the same staging slot. */
+int rc_submit_frames(rc_ctx* ctx, const uint8_t* frames, size_t step, size_t frame_stride, int count, int framecount0,
+                     uint8_t* outmasks, size_t mask_stride, rc_frame_result* results);
+int rc_wait(rc_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -13,8 +13,12 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libripcurrents_b200.so")
 SOURCES = ["farneback.cu", "aggregate.cu", "advect.cu", "api.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall", "-Xptxas", "-v"]
+# farneback.cu holds both arithmetic modes: its strict code is written with __fmul_rn/__fadd_rn intrinsics (never
+# contracted) and its fast code wants FMA contraction; the other files restate reference arithmetic in which every
+# product and sum rounds separately, so they are compiled with contraction off.
+EXTRA = {"farneback.cu": [], "aggregate.cu": ["-fmad=false"], "advect.cu": ["-fmad=false"], "api.cu": ["-fmad=false"]}
 
 
 def _nvcc():
@@ -38,7 +42,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(LIBDIR, s[:-3] + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in _deps(src)):
-            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            cmd = [_nvcc()] + NVCC_FLAGS + EXTRA.get(s, []) + ["-c", src, "-o", obj]
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
             rebuilt = True
     for s, p in procs:

@@ -18,7 +18,8 @@ ADV_PATHLINE, ADV_LEGACY, ADV_MODULE, ADV_CUT5, ADV_FIXED100, ADV_FIELD, ADV_GET
 SYMBOLS = [
     "rc_version", "rc_error_string", "rc_last_error", "rc_kernel_launches", "rc_create", "rc_destroy",
     "rc_set_stream", "rc_synchronize", "rc_profile_enable", "rc_profile_reset", "rc_profile_count", "rc_profile_get",
-    "rc_farneback", "rc_flow_configure", "rc_flow_push", "rc_flow_device",
+    "rc_farneback", "rc_flow_configure", "rc_flow_push", "rc_flow_device", "rc_flow_configure_batch",
+    "rc_flow_push_batch", "rc_flow_device_at", "rc_process_frames", "rc_submit_frames", "rc_wait",
     "rc_hist_reset", "rc_polar_hist", "rc_hist_get", "rc_hist_add", "rc_hist_device", "rc_cart_to_polar",
     "rc_thresholds", "rc_accumulator_reset", "rc_classify_accumulate", "rc_accumulator_get",
     "rc_accumulator_device", "rc_window_configure", "rc_window_update", "rc_window_get", "rc_window_device",
@@ -145,6 +146,34 @@ class Context:
                                              C.c_double(poly_sigma), C.c_int(flags)))
         self.w, self.h_img = w, h
 
+    def flow_configure_batch(self, w, h, pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags, max_batch):
+        self._chk(self.lib.rc_flow_configure_batch(self.h, C.c_int(w), C.c_int(h), C.c_double(pyr_scale),
+                                                   C.c_int(levels), C.c_int(winsize), C.c_int(iterations),
+                                                   C.c_int(poly_n), C.c_double(poly_sigma), C.c_int(flags),
+                                                   C.c_int(max_batch)))
+        self.w, self.h_img = w, h
+
+    def flow_push_batch(self, frames, count=None, flows=None):
+        """frames: numpy (count,h,w) u8 / device pointer to dense frames.  Returns the number of flows produced."""
+        if isinstance(frames, np.ndarray):
+            assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.flags.c_contiguous
+            count = frames.shape[0]
+        n = self.w * self.h_img
+        return self._chk(self.lib.rc_flow_push_batch(self.h, _ptr(frames), C.c_size_t(self.w), C.c_size_t(n),
+                                                     C.c_int(count), _ptr(flows), C.c_size_t(self.w * 8),
+                                                     C.c_size_t(n * 8)))
+
+    def flow_device_at(self, back):
+        p = C.c_void_p()
+        self._chk(self.lib.rc_flow_device_at(self.h, C.c_int(back), C.byref(p)))
+        return p.value
+
+    def flow_host_at(self, back):
+        out = np.empty((self.h_img, self.w, 2), np.float32)
+        self.synchronize()
+        _memcpy_d2h(out, self.flow_device_at(back))
+        return out
+
     def flow_push(self, frame, step=None, flow=None):
         """frame: numpy u8 (host) / torch tensor / raw device pointer.  Returns 1 when a flow was produced."""
         if isinstance(frame, np.ndarray):
@@ -161,6 +190,7 @@ class Context:
     def flow_host(self):
         p, w, h = self.flow_device()
         out = np.empty((h, w, 2), np.float32)
+        self.synchronize()
         _memcpy_d2h(out, p)
         return out
 
@@ -285,6 +315,26 @@ class Context:
         rc = self._chk(self.lib.rc_process_frame(self.h, _ptr(frame), C.c_size_t(step or self.w), C.c_int(framecount),
                                                  _ptr(outmask), C.byref(res) if res is not None else None))
         return rc, res
+
+
+    def process_frames(self, frames, framecount0, outmasks=None, want_results=True, count=None, submit_only=False,
+                       results=None):
+        """frames: numpy (count,h,w) u8 (host) / tensor / device pointer to dense frames.
+        Returns (flows produced, ctypes array of FrameResult or None)."""
+        if isinstance(frames, np.ndarray):
+            assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.flags.c_contiguous
+            count = frames.shape[0]
+        n = self.w * self.h_img
+        if results is None and want_results:
+            results = (FrameResult * count)()
+        fn = self.lib.rc_submit_frames if submit_only else self.lib.rc_process_frames
+        rc = self._chk(fn(self.h, _ptr(frames), C.c_size_t(self.w), C.c_size_t(n), C.c_int(count),
+                          C.c_int(framecount0), _ptr(outmasks), C.c_size_t(n),
+                          C.byref(results) if results is not None else None))
+        return rc, results
+
+    def wait(self):
+        self._chk(self.lib.rc_wait(self.h))
 
 
 _cudart = None

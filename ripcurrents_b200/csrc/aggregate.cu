@@ -79,53 +79,70 @@ __global__ void cart_to_polar_kernel(const float* __restrict__ flow, size_t n, f
     mag[i] = m; ang[i] = a;
 }
 
-// Thresholds (ripcurrents.cpp:333-366).  One warp: lane a < 36 owns direction a; lane 0 also does the global one.
-__global__ void thresholds_kernel(const unsigned long long* __restrict__ hist2d, float* __restrict__ thr)
+// Thresholds (ripcurrents.cpp:333-366) after each frame of a batch: cumulative += delta[j], then the tail scans.
+// One CTA; thread a < 36 owns direction a; thread 0 also does the global threshold.
+__global__ void __launch_bounds__(256)
+thresholds_batch_kernel(unsigned long long* __restrict__ hist2d, const unsigned int* __restrict__ delta, int nb,
+                        float* __restrict__ thr_batch, float* __restrict__ thr_last)
 {
+    __shared__ long long cum[RC_HIST_CELLS];
     __shared__ long long hist[RC_HIST_BINS];
     __shared__ long long s_threshsum;
     __shared__ int s_target;
     const int t = threadIdx.x;
-    if (t < RC_HIST_BINS) {
-        long long s = 0;
-        for (int a = 0; a < RC_HIST_ROWS; a++) s += (long long)hist2d[a * RC_HIST_BINS + t];
-        hist[t] = s;
-    }
+    for (int i = t; i < RC_HIST_CELLS; i += blockDim.x) cum[i] = (long long)hist2d[i];
     __syncthreads();
-    if (t == 0) {
-        long long histsum = 0;
-        for (int b = 0; b < RC_HIST_BINS; b++) histsum += hist[b];
-        long long threshsum = 0;
-        int bin = RC_HIST_BINS - 1;
-        while ((double)threshsum < ((double)histsum * .05)) { threshsum += hist[bin]; bin--; }
-        thr[0] = __fdiv_rn((float)bin, (float)RC_HIST_RESOLUTION);
-        s_threshsum = threshsum; s_target = bin;
-        reinterpret_cast<long long*>(thr + 74)[0] = histsum;   // 8-byte aligned slot after the 73 floats
+    const int nframes = nb > 0 ? nb : 1;
+    for (int j = 0; j < nframes; j++) {
+        if (nb > 0) {
+            for (int i = t; i < RC_HIST_CELLS; i += blockDim.x) cum[i] += (long long)delta[(size_t)j * RC_HIST_CELLS + i];
+            __syncthreads();
+        }
+        float* thr = thr_batch ? thr_batch + (size_t)j * RC_THR_FLOATS : thr_last;
+        if (t < RC_HIST_BINS) {
+            long long s = 0;
+            for (int a = 0; a < RC_HIST_ROWS; a++) s += cum[a * RC_HIST_BINS + t];
+            hist[t] = s;
+        }
+        __syncthreads();
+        if (t == 0) {
+            long long histsum = 0;
+            for (int b = 0; b < RC_HIST_BINS; b++) histsum += hist[b];
+            long long threshsum = 0;
+            int bin = RC_HIST_BINS - 1;
+            while ((double)threshsum < ((double)histsum * .05)) { threshsum += hist[bin]; bin--; }
+            thr[0] = __fdiv_rn((float)bin, (float)RC_HIST_RESOLUTION);
+            s_threshsum = threshsum; s_target = bin;
+            reinterpret_cast<long long*>(thr + 74)[0] = histsum;   // 8-byte aligned slot after the 73 floats
+        }
+        __syncthreads();
+        if (t < RC_HIST_DIRECTIONS) {
+            const long long* row = cum + t * RC_HIST_BINS;
+            long long sum = 0;
+            for (int b = 0; b < RC_HIST_BINS; b++) sum += row[b];
+            long long t2 = 0, t3 = 0;
+            int b = RC_HIST_BINS - 1;
+            while ((double)t2 < ((double)sum * .05)) { t2 += row[b]; b--; }
+            float u = __fdiv_rn((float)b, (float)RC_HIST_RESOLUTION);
+            if ((double)u < 0.01) u = (float)0.01;
+            thr[1 + t] = u;
+            b = RC_HIST_BINS - 1;
+            while (b > s_target) { t3 += row[b]; b--; }
+            thr[37 + t] = __fdiv_rn((float)t3, (float)s_threshsum);
+        }
+        __syncthreads();
+        if (thr_batch && thr_last && j == nframes - 1)
+            for (int i = t; i < RC_THR_FLOATS; i += blockDim.x) thr_last[i] = thr[i];
     }
-    __syncthreads();
-    if (t < RC_HIST_DIRECTIONS) {
-        const unsigned long long* row = hist2d + t * RC_HIST_BINS;
-        long long sum = 0;
-        for (int b = 0; b < RC_HIST_BINS; b++) sum += (long long)row[b];
-        long long t2 = 0, t3 = 0;
-        int b = RC_HIST_BINS - 1;
-        while ((double)t2 < ((double)sum * .05)) { t2 += (long long)row[b]; b--; }
-        float u = __fdiv_rn((float)b, (float)RC_HIST_RESOLUTION);
-        if ((double)u < 0.01) u = (float)0.01;
-        thr[1 + t] = u;
-        b = RC_HIST_BINS - 1;
-        while (b > s_target) { t3 += (long long)row[b]; b--; }
-        thr[37 + t] = __fdiv_rn((float)t3, (float)s_threshsum);
-    }
+    if (nb > 0)
+        for (int i = t; i < RC_HIST_CELLS; i += blockDim.x) hist2d[i] = (unsigned long long)cum[i];
 }
 
-// classify (mag > UPPER -> accumulator2.x = 1), accumulate when framecount > 30, mask/out classes; optionally the
-// sliding-window update of main.cpp:1143-1153 on the same read of the flow.
+// classify (mag > UPPER -> accumulator2.x = 1), accumulate when framecount > 30, mask/out classes: single frame
 __global__ void __launch_bounds__(256)
 classify_kernel(const float* __restrict__ flow, size_t flow_step, int w, int h, float upper_arg,
                 const float* __restrict__ thr, int framecount, float* __restrict__ acc, uint8_t* __restrict__ mask,
-                uint8_t* __restrict__ waveclass, uint8_t* __restrict__ waterclass, float* __restrict__ ring_slot,
-                float* __restrict__ avg, float inv_w)
+                uint8_t* __restrict__ waveclass, uint8_t* __restrict__ waterclass)
 {
     const size_t n = (size_t)w * h;
     const float upper = isnan(upper_arg) ? thr[0] : upper_arg;
@@ -148,14 +165,83 @@ classify_kernel(const float* __restrict__ flow, size_t flow_step, int w, int h, 
         if (mask) mask[i] = wave ? 0 : 255;
         if (waveclass) waveclass[i] = wave ? (((double)val < hi) ? 1 : 2) : 0;
         if (waterclass) waterclass[i] = m > upper ? 3 : (m > 0.5f ? 2 : (m > 0.2f ? 1 : 0));
+    }
+}
+
+// Batched classify + accumulate + mask + sliding-window mean: each thread owns 4 adjacent pixels and walks the
+// nb frames of the batch in order, keeping accumulator.x and the window mean in registers -- they are read and
+// written ONCE per batch instead of once per frame.  Per frame and pixel: 8 B flow + 8 B leaving ring slot read,
+// 1 B mask written.  (ripcurrents.cpp:376-439 + main.cpp:1143-1153, in the reference's order.)
+__global__ void __launch_bounds__(256)
+classify_batch_kernel(ClassifyBatch cb, size_t n4, size_t n, const float* __restrict__ thr_batch, int framecount0,
+                      float* __restrict__ acc, uint8_t* __restrict__ masks, float* __restrict__ avg, float inv_w)
+{
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= n4) return;
+    const size_t i = i4 * 4;
+    const bool full = i + 3 < n;
+    float av[4]; float2 mean[4];
+    if (full) {
+        float4 t = *reinterpret_cast<const float4*>(acc + i);
+        av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
         if (avg) {
-            float2* rs = reinterpret_cast<float2*>(ring_slot) + i;
-            float2* ap = reinterpret_cast<float2*>(avg) + i;
-            float2 o = *rs, v = *ap;
-            v.x = (v.x - o.x * inv_w) + f.x * inv_w;
-            v.y = (v.y - o.y * inv_w) + f.y * inv_w;
-            *rs = f; *ap = v;
+            float4 m0 = *reinterpret_cast<const float4*>(avg + 2 * i), m1 = *reinterpret_cast<const float4*>(avg + 2 * i + 4);
+            mean[0] = make_float2(m0.x, m0.y); mean[1] = make_float2(m0.z, m0.w);
+            mean[2] = make_float2(m1.x, m1.y); mean[3] = make_float2(m1.z, m1.w);
         }
+    } else {
+        for (int k = 0; k < 4; k++) {
+            av[k] = i + k < n ? acc[i + k] : 0.f;
+            mean[k] = (avg && i + k < n) ? reinterpret_cast<const float2*>(avg)[i + k] : make_float2(0.f, 0.f);
+        }
+    }
+    for (int j = 0; j < cb.nb; j++) {
+        const float upper = thr_batch[(size_t)j * RC_THR_FLOATS];
+        const int fc = framecount0 + j;
+        const double lo = .1 * fc;
+        float2 f[4], o[4];
+        if (full) {
+            float4 a = __ldcs(reinterpret_cast<const float4*>(cb.flow[j] + 2 * i));
+            float4 b = __ldcs(reinterpret_cast<const float4*>(cb.flow[j] + 2 * i + 4));
+            f[0] = make_float2(a.x, a.y); f[1] = make_float2(a.z, a.w); f[2] = make_float2(b.x, b.y); f[3] = make_float2(b.z, b.w);
+            if (avg && cb.old[j]) {
+                float4 c = __ldcs(reinterpret_cast<const float4*>(cb.old[j] + 2 * i));
+                float4 d = __ldcs(reinterpret_cast<const float4*>(cb.old[j] + 2 * i + 4));
+                o[0] = make_float2(c.x, c.y); o[1] = make_float2(c.z, c.w); o[2] = make_float2(d.x, d.y); o[3] = make_float2(d.z, d.w);
+            } else { o[0] = o[1] = o[2] = o[3] = make_float2(0.f, 0.f); }
+        } else {
+            for (int k = 0; k < 4; k++) {
+                f[k] = i + k < n ? reinterpret_cast<const float2*>(cb.flow[j])[i + k] : make_float2(0.f, 0.f);
+                o[k] = (avg && cb.old[j] && i + k < n) ? reinterpret_cast<const float2*>(cb.old[j])[i + k] : make_float2(0.f, 0.f);
+            }
+        }
+        unsigned char mk[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float m, a;
+            cart_to_polar(f[k].x, f[k].y, m, a);
+            if (fc > 30) av[k] = (m > upper ? 1.f : 0.f) + av[k];
+            mk[k] = ((double)(int)av[k] > lo) ? 0 : 255;
+            if (avg) {
+                mean[k].x = (mean[k].x - o[k].x * inv_w) + f[k].x * inv_w;
+                mean[k].y = (mean[k].y - o[k].y * inv_w) + f[k].y * inv_w;
+            }
+        }
+        if (masks) {
+            uint8_t* mrow = masks + (size_t)j * n;
+            if (full) *reinterpret_cast<uchar4*>(mrow + i) = make_uchar4(mk[0], mk[1], mk[2], mk[3]);
+            else for (int k = 0; k < 4; k++) if (i + k < n) mrow[i + k] = mk[k];
+        }
+    }
+    if (full) {
+        *reinterpret_cast<float4*>(acc + i) = make_float4(av[0], av[1], av[2], av[3]);
+        if (avg) {
+            *reinterpret_cast<float4*>(avg + 2 * i) = make_float4(mean[0].x, mean[0].y, mean[1].x, mean[1].y);
+            *reinterpret_cast<float4*>(avg + 2 * i + 4) = make_float4(mean[2].x, mean[2].y, mean[3].x, mean[3].y);
+        }
+    } else {
+        for (int k = 0; k < 4; k++)
+            if (i + k < n) { acc[i + k] = av[k]; if (avg) reinterpret_cast<float2*>(avg)[i + k] = mean[k]; }
     }
 }
 
@@ -233,21 +319,32 @@ void rc_launch_cart_to_polar(rc_ctx* c, const float* flow, size_t n, float* mag,
     cart_to_polar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(flow, n, mag, ang);
 }
 
-void rc_launch_thresholds(rc_ctx* c, const unsigned long long* hist2d, float* thr)
+void rc_launch_thresholds_batch(rc_ctx* c, unsigned long long* hist2d, const unsigned int* delta, int nb,
+                                float* thr_batch, float* thr_last)
 {
-    KScope ks(c, K_THRESHOLDS, 8.0 * RC_HIST_ROWS * RC_HIST_BINS);
-    thresholds_kernel<<<1, 64, 0, c->stream>>>(hist2d, thr);
+    KScope ks(c, K_THRESHOLDS, (8.0 + 4.0 * nb) * RC_HIST_CELLS);
+    thresholds_batch_kernel<<<1, 256, 0, c->stream>>>(hist2d, delta, nb, thr_batch, thr_last);
 }
 
 void rc_launch_classify(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float upper, const float* thr,
-                        int framecount, float* acc, uint8_t* mask, uint8_t* waveclass, uint8_t* waterclass,
-                        float* ring_slot, float* avg, int W)
+                        int framecount, float* acc, uint8_t* mask, uint8_t* waveclass, uint8_t* waterclass)
 {
     const size_t n = (size_t)w * h;
-    const float inv = W > 0 ? (float)(1.0 / (double)W) : 0.f;
-    KScope ks(c, K_CLASSIFY, (8.0 + 8.0 + (mask ? 1.0 : 0.0) + (avg ? 32.0 : 0.0)) * n);
+    KScope ks(c, K_CLASSIFY, (8.0 + 8.0 + (mask ? 1.0 : 0.0)) * n);
     classify_kernel<<<grid_for(n, 256, 8), 256, 0, c->stream>>>(flow, flow_step, w, h, upper, thr, framecount, acc, mask,
-                                                               waveclass, waterclass, ring_slot, avg, inv);
+                                                               waveclass, waterclass);
+}
+
+void rc_launch_classify_batch(rc_ctx* c, const ClassifyBatch& cb, int w, int h, const float* thr_batch, int framecount0,
+                              float* acc, uint8_t* masks, float* avg, int W)
+{
+    const size_t n = (size_t)w * h, n4 = (n + 3) / 4;
+    const float inv = W > 0 ? (float)(1.0 / (double)W) : 0.f;
+    int nold = 0;
+    for (int j = 0; j < cb.nb; j++) nold += (avg && cb.old[j]) ? 1 : 0;
+    KScope ks(c, K_CLASSIFY, ((8.0 + (masks ? 1.0 : 0.0)) * cb.nb + 8.0 * nold + 8.0 + (avg ? 16.0 : 0.0)) * n);
+    classify_batch_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, c->stream>>>(cb, n4, n, thr_batch, framecount0, acc, masks,
+                                                                              avg, inv);
 }
 
 void rc_launch_window_update(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float* slot, float* avg, int W)

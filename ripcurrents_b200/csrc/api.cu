@@ -7,11 +7,11 @@
 
 #include "rc_internal.h"
 
-#define RC_VERSION 100
+#define RC_VERSION 101
 
 const char* const rc_kernel_names[K_COUNT] = {"pyr_h", "pyr_v", "polyexp", "update_matrices", "flow_iter_fused",
-                                              "flow_iter_final", "polar_hist", "thresholds", "classify", "window_mean",
-                                              "advect", "streakline", "misc"};
+                                              "flow_iter_final", "flow_layer_fused", "polar_hist", "thresholds",
+                                              "classify", "window_mean", "advect", "streakline", "misc"};
 
 namespace {
 
@@ -60,33 +60,41 @@ int dev_alloc(rc_ctx* c, void** p, size_t bytes)
 {
     if (cudaMalloc(p, bytes < 256 ? 256 : bytes) != cudaSuccess) {
         cudaGetLastError();
+        *p = nullptr;
         return fail(c, RC_ERR_NOMEM, "cudaMalloc failed%s");
     }
     c->allocs.push_back(*p);
     return RC_OK;
 }
 
+void sync_all(rc_ctx* c)
+{
+    if (c->s_in) cudaStreamSynchronize(c->s_in);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->s_out) cudaStreamSynchronize(c->s_out);
+}
+
 void free_farneback(rc_ctx* c)
 {
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    sync_all(c);
     for (void* p : c->allocs) cudaFree(p);
     c->allocs.clear();
     for (auto& L : c->layer) L = Layer();
-    c->configured = false; c->nlayers = 0; c->frames_seen = 0; c->have_flow = false; c->flow_out = nullptr;
+    for (int s = 0; s < 2; s++) {
+        c->d_frames[s] = nullptr; c->d_masks[s] = nullptr; c->d_thr_batch[s] = nullptr;
+        if (c->h_thr[s]) { cudaFreeHost(c->h_thr[s]); c->h_thr[s] = nullptr; }
+        c->pending_results[s] = nullptr; c->pending_count[s] = 0;
+    }
+    c->flow_ring = nullptr; c->ring_slots = 0; c->d_avg = nullptr; c->d_hist_delta = nullptr;
+    c->configured = false; c->nlayers = 0; c->frames_seen = 0; c->n_flows = 0; c->pairs_done = 0; c->submitted = 0;
 }
 
 int round_half_even(double v) { return (int)nearbyint(v); }
 
-int alloc_planes(rc_ctx* c, Planes& P, int w, int h)
-{
-    P.w = w; P.h = h; P.pitch = (w + 31) / 32 * 32;
-    P.pstride = (size_t)P.pitch * h;
-    return dev_alloc(c, (void**)&P.p, sizeof(float) * P.pstride * 5);
-}
-
 // Appendix A.3 kernels and the closed-form inverse of the moment matrix
 void make_poly(PolyCoef& pc, int n, double sigma, bool strict)
 {
+    memset(&pc, 0, sizeof pc);
     if (sigma < FLT_EPSILON) sigma = n * 0.3;
     std::vector<float> G(2 * n + 1);
     double s = 0;
@@ -112,15 +120,16 @@ void make_poly(PolyCoef& pc, int n, double sigma, bool strict)
     pc.n = n;
     pc.n_eff = n;
     if (!strict) {
-        // drop taps whose x^2-weighted contribution is below 1e-12 of the centre weight
+        // fast mode: drop taps whose x^2-weighted weight is below 1e-9 of the centre weight (invisible in fp32)
         int k = n;
-        while (k > 1 && (double)pc.xxg[k] < 1e-12 * (double)pc.g[0]) k--;
+        while (k > 1 && (double)pc.xxg[k] < 1e-9 * (double)pc.g[0]) k--;
         pc.n_eff = k;
     }
 }
 
 void make_smooth(SmoothCoef& sc, double sigma, int ksize)
 {
+    memset(&sc, 0, sizeof sc);
     sc.ksize = ksize;
     if (sigma <= 0 && ksize == 3) { sc.k[0] = 0.25f; sc.k[1] = 0.5f; sc.k[2] = 0.25f; return; }
     if (sigma <= 0) sigma = ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8;
@@ -131,22 +140,30 @@ void make_smooth(SmoothCoef& sc, double sigma, int ksize)
     for (int i = 0; i < ksize; i++) sc.k[i] = (float)(t[i] * sum);
 }
 
-void make_gwin(GaussWin& g, int winsize)
+void make_win(WinCoef& g, int winsize, bool gaussian)
 {
+    memset(&g, 0, sizeof g);
     int m = winsize / 2;
+    g.m = m; g.gaussian = gaussian ? 1 : 0;
+    if (!gaussian) {
+        for (int i = 0; i <= m; i++) g.k[i] = 1.f;
+        g.post_scale_d = 1.0 / ((double)winsize * winsize);
+        g.post_scale = (float)g.post_scale_d;
+        return;
+    }
     double sigma = m * 0.3, s = 1.0;
-    g.m = m;
     g.k[0] = 1.f;
     for (int i = 1; i <= m; i++) { float t = (float)exp(-i * i / (2 * sigma * sigma)); g.k[i] = t; s += t * 2; }
     s = 1.0 / s;
     for (int i = 0; i <= m; i++) g.k[i] = (float)(g.k[i] * s);
+    g.post_scale = 1.f; g.post_scale_d = 1.0;
 }
 
 int ensure_aggregate(rc_ctx* c)
 {
     if (c->d_hist2d) return RC_OK;
-    CUDA_TRY(c, cudaMalloc((void**)&c->d_hist2d, sizeof(unsigned long long) * RC_HIST_ROWS * RC_HIST_BINS));
-    CUDA_TRY(c, cudaMemsetAsync(c->d_hist2d, 0, sizeof(unsigned long long) * RC_HIST_ROWS * RC_HIST_BINS, c->stream));
+    CUDA_TRY(c, cudaMalloc((void**)&c->d_hist2d, sizeof(unsigned long long) * RC_HIST_CELLS));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_hist2d, 0, sizeof(unsigned long long) * RC_HIST_CELLS, c->stream));
     CUDA_TRY(c, cudaMalloc((void**)&c->d_thr, sizeof(float) * RC_THR_FLOATS));
     CUDA_TRY(c, cudaMemsetAsync(c->d_thr, 0, sizeof(float) * RC_THR_FLOATS, c->stream));
     return RC_OK;
@@ -155,24 +172,46 @@ int ensure_aggregate(rc_ctx* c)
 int ensure_accumulator(rc_ctx* c, int w, int h)
 {
     if (c->d_acc && c->acc_w == w && c->acc_h == h) return RC_OK;
-    if (c->d_acc) { cudaStreamSynchronize(c->stream); cudaFree(c->d_acc); cudaFree(c->d_mask); cudaFree(c->d_cls); }
-    c->d_acc = nullptr; c->d_mask = nullptr; c->d_cls = nullptr;
+    if (c->d_acc) { sync_all(c); cudaFree(c->d_acc); cudaFree(c->d_cls); }
+    c->d_acc = nullptr; c->d_cls = nullptr;
     const size_t n = (size_t)w * h;
-    CUDA_TRY(c, cudaMalloc((void**)&c->d_acc, sizeof(float) * n));
-    CUDA_TRY(c, cudaMalloc((void**)&c->d_mask, n));
-    CUDA_TRY(c, cudaMalloc((void**)&c->d_cls, 2 * n));
-    CUDA_TRY(c, cudaMemsetAsync(c->d_acc, 0, sizeof(float) * n, c->stream));
+    CUDA_TRY(c, cudaMalloc((void**)&c->d_acc, sizeof(float) * (n + 4)));
+    CUDA_TRY(c, cudaMalloc((void**)&c->d_cls, 3 * n));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_acc, 0, sizeof(float) * (n + 4), c->stream));
     c->acc_w = w; c->acc_h = h;
     return RC_OK;
 }
 
-// Brings a (possibly host, possibly strided) flow field to the device as a dense w*h*2 array when needed.
-// Returns the device pointer + step to use.
+// (Re)allocates the layer-0 flow ring: W + B slots so that the flow leaving a W-frame window is still resident
+// while a batch of up to B new flows is written.
+int ensure_flow_ring(rc_ctx* c)
+{
+    const int want = (c->win_W > 0 ? c->win_W : 0) + c->B;
+    if (c->flow_ring && c->ring_slots == want) return RC_OK;
+    const size_t per = sizeof(float) * 2 * (size_t)c->prm.w * c->prm.h;
+    sync_all(c);
+    int rc;
+    // (an older ring, if any, stays in `allocs` until the context is reconfigured: window changes are rare)
+    if ((rc = dev_alloc(c, (void**)&c->flow_ring, per * want + 64))) return rc;
+    if (!c->d_avg && (rc = dev_alloc(c, (void**)&c->d_avg, per + 64))) return rc;
+    CUDA_TRY(c, cudaMemsetAsync(c->flow_ring, 0, per * want, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_avg, 0, per, c->stream));
+    c->ring_slots = want;
+    c->pairs_done = 0;
+    return RC_OK;
+}
+
+float* ring_slot(rc_ctx* c, long long pair)
+{
+    return c->flow_ring + (size_t)(pair % c->ring_slots) * 2 * (size_t)c->prm.w * c->prm.h;
+}
+
+// Brings a (possibly host, possibly strided) flow field to the device when needed.
 int stage_flow_in(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, const float** d_flow, size_t* d_step)
 {
     if (!flow) {
-        if (!c->have_flow) return fail(c, RC_ERR_STATE, "no flow has been computed on this context%s");
-        *d_flow = c->flow_out; *d_step = (size_t)c->prm.w * 8;
+        if (!c->pairs_done) return fail(c, RC_ERR_STATE, "no flow has been computed on this context%s");
+        *d_flow = ring_slot(c, c->pairs_done - 1); *d_step = (size_t)c->prm.w * 8;
         return RC_OK;
     }
     if (w <= 0 || h <= 0 || flow_step < (size_t)w * 8) return fail(c, RC_ERR_INVALID, "bad flow geometry%s");
@@ -185,19 +224,7 @@ int stage_flow_in(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, 
     return RC_OK;
 }
 
-int copy_out(rc_ctx* c, void* dst, size_t dst_step, const void* d_src, size_t src_step, size_t row_bytes, int rows,
-             bool* host_written)
-{
-    const bool dev = is_device_ptr(dst);
-    CUDA_TRY(c, cudaMemcpy2DAsync(dst, dst_step, d_src, src_step, row_bytes, rows,
-                                  dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
-    if (!dev) *host_written = true;
-    return RC_OK;
-}
-
-}  // namespace
-
-static void prof_drain(rc_ctx* c)
+void prof_drain(rc_ctx* c)
 {
     if (c->prof.empty()) return;
     cudaStreamSynchronize(c->stream);
@@ -211,6 +238,79 @@ static void prof_drain(rc_ctx* c)
     c->prof.clear();
 }
 
+// Expands + computes flows for `count` device-resident frames (rows of `step` bytes, frames `fstride` apart),
+// in sub-batches of at most B.  Returns the number of flows produced (count, or count-1 when priming).
+// With `aggregate` each sub-batch is followed, in stream order, by thresholds + classify (+ window); the per-frame
+// threshold records / masks go to thr_out / masks_out (device, indexed by produced flow).
+int run_frames(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, int count, bool aggregate,
+               int framecount0, float* thr_out, uint8_t* masks_out)
+{
+    const int w = c->prm.w, h = c->prm.h, B = c->B, nslots = B + 1;
+    const size_t n = (size_t)w * h;
+    int produced = 0, done = 0;
+    if (c->frames_seen == 0 && count > 0) {           // priming frame: expand only
+        rc_launch_expand(c, d_frames, step, fstride, 1, c->r_base);
+        c->frames_seen = 1; done = 1;
+    }
+    while (done < count) {
+        const int nb = count - done < B ? count - done : B;
+        const int first = (c->r_base + 1) % nslots;
+        rc_launch_expand(c, d_frames + (size_t)done * fstride, step, fstride, nb, first);
+        float* dst[RC_MAX_BATCH];
+        for (int j = 0; j < nb; j++) dst[j] = ring_slot(c, c->pairs_done + j);
+        rc_launch_flows(c, nb, c->r_base, dst, aggregate ? c->d_hist_delta : nullptr);
+        if (aggregate) {
+            float* thr = thr_out + (size_t)produced * RC_THR_FLOATS;
+            rc_launch_thresholds_batch(c, c->d_hist2d, c->d_hist_delta, nb, thr, c->d_thr);
+            ClassifyBatch cb;
+            cb.nb = nb;
+            for (int j = 0; j < nb; j++) {
+                cb.flow[j] = dst[j];
+                const long long p = c->pairs_done + j;
+                cb.old[j] = (c->win_W > 0 && p >= c->win_W) ? ring_slot(c, p - c->win_W) : nullptr;
+            }
+            // framecount of a flow = the caller's loop counter of the frame that completed the pair
+            rc_launch_classify_batch(c, cb, w, h, thr, framecount0 + done, c->d_acc,
+                                     masks_out ? masks_out + (size_t)produced * n : nullptr,
+                                     c->win_W > 0 ? c->d_avg : nullptr, c->win_W);
+        }
+        c->r_base = (c->r_base + nb) % nslots;
+        c->pairs_done += nb; c->frames_seen += nb;
+        produced += nb; done += nb;
+    }
+    c->n_flows = produced;
+    return produced;
+}
+
+void fill_results(const float* h_thr, int produced, int first_produced, int count, rc_frame_result* results)
+{
+    if (!results) return;
+    memset(results, 0, sizeof(rc_frame_result) * count);
+    for (int i = 0; i < count; i++) {
+        const int j = i - first_produced;             // index among the produced flows
+        if (j < 0 || j >= produced) continue;
+        const float* t = h_thr + (size_t)j * RC_THR_FLOATS;
+        results[i].produced = 1;
+        results[i].UPPER = t[0];
+        memcpy(results[i].UPPER2d, t + 1, sizeof(float) * RC_HIST_DIRECTIONS);
+        memcpy(results[i].prop_above_upper, t + 37, sizeof(float) * RC_HIST_DIRECTIONS);
+        memcpy(&results[i].histsum, t + 74, sizeof(int64_t));
+    }
+}
+
+// Finishes the batch staged in `slot`: waits for its D2H copies and fills the caller's result records.
+int finish_slot(rc_ctx* c, int slot)
+{
+    if (!c->pending_count[slot]) return RC_OK;
+    CUDA_TRY(c, cudaEventSynchronize(c->ev_out[slot]));
+    const int count = c->pending_count[slot];
+    const int first = c->pending_first_produced[slot];
+    fill_results(c->h_thr[slot], count - first, first, count, c->pending_results[slot]);
+    c->pending_count[slot] = 0; c->pending_results[slot] = nullptr;
+    return RC_OK;
+}
+
+}  // namespace
 
 // =====================================================================================================
 extern "C" {
@@ -244,9 +344,14 @@ int rc_create(rc_ctx** out, int device)
     rc_ctx* c = new (std::nothrow) rc_ctx();
     if (!c) return RC_ERR_NOMEM;
     c->device = device;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        cudaGetLastError(); delete c; return RC_ERR_CUDA;
-    }
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int s = 0; ok && s < 2; s++)
+        ok = cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_compute[s], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_out[s], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); delete c; return RC_ERR_CUDA; }
     c->own_stream = true;
     *out = c;
     return RC_OK;
@@ -257,13 +362,17 @@ void rc_destroy(rc_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     free_farneback(c);
-    if (c->stream) cudaStreamSynchronize(c->stream);
-    void* bufs[] = {c->d_frame, c->d_tmp, c->d_tmp2, c->d_hist2d, c->d_thr, c->d_acc, c->d_mask, c->d_cls, c->d_ring,
-                    c->d_avg};
+    void* bufs[] = {c->d_tmp, c->d_tmp2, c->d_hist2d, c->d_thr, c->d_acc, c->d_cls, c->d_swin_ring, c->d_swin_avg};
     for (void* p : bufs) if (p) cudaFree(p);
-    if (c->h_pin) cudaFreeHost(c->h_pin);
     prof_drain(c);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (int s = 0; s < 2; s++) {
+        if (c->ev_in[s]) cudaEventDestroy(c->ev_in[s]);
+        if (c->ev_compute[s]) cudaEventDestroy(c->ev_compute[s]);
+        if (c->ev_out[s]) cudaEventDestroy(c->ev_out[s]);
+    }
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -272,7 +381,7 @@ int rc_set_stream(rc_ctx* c, void* s)
 {
     if (!c) return RC_ERR_INVALID;
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    sync_all(c);
     if (c->own_stream && c->stream) { cudaStreamDestroy(c->stream); c->own_stream = false; c->stream = nullptr; }
     if (!s) {
         CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -286,7 +395,10 @@ int rc_set_stream(rc_ctx* c, void* s)
 int rc_synchronize(rc_ctx* c)
 {
     if (!c) return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_in));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_out));
     return RC_OK;
 }
 
@@ -324,8 +436,8 @@ int rc_profile_get(rc_ctx* c, int idx, const char** name, double* total_ms, int6
 }
 
 // ---- A1 -----------------------------------------------------------------------------------------------
-int rc_flow_configure(rc_ctx* c, int w, int h, double pyr_scale, int levels, int winsize, int iterations, int poly_n,
-                      double poly_sigma, int flags)
+int rc_flow_configure_batch(rc_ctx* c, int w, int h, double pyr_scale, int levels, int winsize, int iterations,
+                            int poly_n, double poly_sigma, int flags, int max_batch)
 {
     if (!c) return RC_ERR_INVALID;
     cudaSetDevice(c->device);
@@ -335,101 +447,114 @@ int rc_flow_configure(rc_ctx* c, int w, int h, double pyr_scale, int levels, int
     if (poly_n < 1 || poly_n > RC_MAX_POLY_N) return fail(c, RC_ERR_UNSUPPORTED, "poly_n must be in [1,32]%s");
     if (winsize < 1 || winsize / 2 > RC_MAX_WIN_HALF) return fail(c, RC_ERR_UNSUPPORTED, "winsize must be in [1,129]%s");
     if (iterations < 1) return fail(c, RC_ERR_UNSUPPORTED, "iterations must be >= 1%s");
+    if (max_batch < 1 || max_batch > RC_MAX_BATCH) return fail(c, RC_ERR_INVALID, "max_batch must be in [1,64]%s");
     FarnebackParams p;
     p.w = w; p.h = h; p.pyr_scale = pyr_scale; p.levels = levels; p.winsize = winsize; p.iterations = iterations;
-    p.poly_n = poly_n; p.poly_sigma = poly_sigma; p.flags = flags;
-    if (c->configured && c->prm == p) { c->frames_seen = 0; c->have_flow = false; return RC_OK; }
+    p.poly_n = poly_n; p.poly_sigma = poly_sigma; p.flags = flags; p.max_batch = max_batch;
+    if (c->configured && c->prm == p) {
+        sync_all(c);
+        c->frames_seen = 0; c->n_flows = 0;
+        return RC_OK;
+    }
     free_farneback(c);
+    c->prm = p; c->B = max_batch;
+    const int B = max_batch;
 
     // Appendix A.1: layer selection
     int k; double scale = 1.0;
     for (k = 0; k < levels; k++) { scale *= pyr_scale; if (w * scale < 32 || h * scale < 32) break; }
     const int nl = k + 1;
     if (nl > RC_MAX_LAYERS) return fail(c, RC_ERR_UNSUPPORTED, "too many pyramid layers%s");
+    c->strict = (flags & RC_FARNEBACK_STRICT) != 0;
     scale = 1.0;
-    for (k = 0; k < nl; k++) {
+    int rc = RC_OK;
+    for (k = 0; k < nl && !rc; k++) {
         Layer& L = c->layer[k];
         L.w = round_half_even(w * scale); L.h = round_half_even(h * scale);
+        L.pitch = (L.w + 31) / 32 * 32;
+        L.plane = (size_t)L.pitch * L.h;
         double sigma = (1.0 / scale - 1.0) * 0.5;
         int ks = round_half_even(sigma * 5.0) | 1; if (ks < 3) ks = 3;
-        if (ks > RC_MAX_SMOOTH_TAPS) { free_farneback(c); return fail(c, RC_ERR_UNSUPPORTED, "pyramid too deep (smoothing kernel > 255 taps)%s"); }
+        if (ks > RC_MAX_SMOOTH_TAPS) { rc = fail(c, RC_ERR_UNSUPPORTED, "pyramid too deep (smoothing kernel > 255 taps)%s"); break; }
         make_smooth(L.smooth, sigma, ks);
-        const int pitch = (L.w + 31) / 32 * 32;
-        int rc;
-        if ((rc = dev_alloc(c, (void**)&L.I, sizeof(float) * (size_t)pitch * L.h)) ||
-            (rc = dev_alloc(c, (void**)&L.htmp, sizeof(float) * 2 * (size_t)L.w * h)) ||
-            (rc = alloc_planes(c, L.R[0], L.w, L.h)) || (rc = alloc_planes(c, L.R[1], L.w, L.h)) ||
-            (rc = alloc_planes(c, L.M[0], L.w, L.h)) || (rc = alloc_planes(c, L.M[1], L.w, L.h)) ||
-            (rc = dev_alloc(c, (void**)&L.flow, sizeof(float) * 2 * (size_t)L.w * L.h))) {
-            free_farneback(c);
-            return rc;
-        }
+        L.htmp_stride = 2 * (size_t)L.w * h;
+        const bool fused = !c->strict && winsize / 2 == 1 && iterations <= 3;
+        if ((rc = dev_alloc(c, (void**)&L.I, sizeof(float) * L.plane * B)) ||
+            (rc = dev_alloc(c, (void**)&L.htmp, sizeof(float) * L.htmp_stride * B)) ||
+            (rc = dev_alloc(c, (void**)&L.R, sizeof(float) * 5 * L.plane * (B + 1))) ||
+            (!fused && (rc = dev_alloc(c, (void**)&L.M, sizeof(float) * 2 * 5 * L.plane * B))) ||
+            (k > 0 && (rc = dev_alloc(c, (void**)&L.flow, sizeof(float) * 2 * (size_t)L.w * L.h * B))))
+            break;
         scale *= pyr_scale;
     }
+    const size_t n = (size_t)w * h;
+    for (int s = 0; s < 2 && !rc; s++) {
+        if ((rc = dev_alloc(c, (void**)&c->d_frames[s], n * B + 64)) || (rc = dev_alloc(c, (void**)&c->d_masks[s], n * B + 64)) ||
+            (rc = dev_alloc(c, (void**)&c->d_thr_batch[s], sizeof(float) * RC_THR_FLOATS * B)))
+            break;
+        if (cudaMallocHost((void**)&c->h_thr[s], sizeof(float) * RC_THR_FLOATS * B) != cudaSuccess) {
+            cudaGetLastError(); rc = fail(c, RC_ERR_NOMEM, "cudaMallocHost failed%s");
+        }
+    }
+    if (!rc) rc = dev_alloc(c, (void**)&c->d_hist_delta, sizeof(unsigned int) * RC_HIST_CELLS * B);
+    if (rc) { free_farneback(c); return rc; }
     c->nlayers = nl;
-    make_poly(c->poly, poly_n, poly_sigma, (flags & RC_FARNEBACK_STRICT) != 0);
-    make_gwin(c->gwin, winsize);
-    c->prm = p; c->configured = true; c->frames_seen = 0; c->have_flow = false; c->cur = 0;
-    c->flow_out = c->layer[0].flow;
+    make_poly(c->poly, poly_n, poly_sigma, c->strict);
+    make_win(c->win, winsize, (flags & RC_FARNEBACK_GAUSSIAN) != 0);
+    c->configured = true; c->frames_seen = 0; c->n_flows = 0; c->r_base = 0; c->pairs_done = 0; c->submitted = 0;
+    if (c->win_W > 0 && (c->swin_w != w || c->swin_h != h)) c->win_W = 0;
+    rc = ensure_flow_ring(c);
+    if (rc) { free_farneback(c); return rc; }
     return RC_OK;
 }
 
-static int flow_push_impl(rc_ctx* c, const uint8_t* frame, size_t step)
+int rc_flow_configure(rc_ctx* c, int w, int h, double pyr_scale, int levels, int winsize, int iterations, int poly_n,
+                      double poly_sigma, int flags)
 {
+    return rc_flow_configure_batch(c, w, h, pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags, 1);
+}
+
+int rc_flow_push_batch(rc_ctx* c, const uint8_t* frames, size_t step, size_t frame_stride, int count, float* flows,
+                       size_t flow_step, size_t flow_stride)
+{
+    if (!c) return RC_ERR_INVALID;
+    if (!c->configured) return fail(c, RC_ERR_STATE, "rc_flow_configure has not been called%s");
+    if (count < 1) return fail(c, RC_ERR_INVALID, "count < 1%s");
+    cudaSetDevice(c->device);
     const int w = c->prm.w, h = c->prm.h;
-    if (!frame || step < (size_t)w) return fail(c, RC_ERR_INVALID, "bad frame pointer / step%s");
-    const uint8_t* d_img = frame; size_t d_step = step;
-    if (!is_device_ptr(frame)) {
-        int rc = ensure(c, (void**)&c->d_frame, &c->d_frame_cap, (size_t)w * h);
-        if (rc) return rc;
-        CUDA_TRY(c, cudaMemcpy2DAsync(c->d_frame, w, frame, step, w, h, cudaMemcpyHostToDevice, c->stream));
-        d_img = c->d_frame; d_step = w;
+    if (!frames || step < (size_t)w || (count > 1 && frame_stride < step * (size_t)(h - 1) + w))
+        return fail(c, RC_ERR_INVALID, "bad frame pointer / step / stride%s");
+    const uint8_t* d = frames; size_t ds = step, dfs = frame_stride;
+    bool host = false;
+    if (!is_device_ptr(frames)) {
+        if (count > c->B) return fail(c, RC_ERR_INVALID, "more host frames than max_batch%s");
+        host = true;
+        for (int j = 0; j < count; j++)
+            CUDA_TRY(c, cudaMemcpy2DAsync(c->d_frames[0] + (size_t)j * w * h, w, frames + (size_t)j * frame_stride, step, w, h,
+                                          cudaMemcpyHostToDevice, c->stream));
+        d = c->d_frames[0]; ds = w; dfs = (size_t)w * h;
     }
-    c->cur ^= 1;
-    const int cur = c->cur, prev = cur ^ 1;
-    for (int k = 0; k < c->nlayers; k++) {
-        Layer& L = c->layer[k];
-        rc_launch_pyr_layer(c, d_img, d_step, w, h, L);
-        rc_launch_polyexp(c, L.I, L.w, L.h, (L.w + 31) / 32 * 32, L.R[cur]);
-    }
+    if (flows && count - (c->frames_seen == 0 ? 1 : 0) > c->ring_slots)
+        return fail(c, RC_ERR_INVALID, "more flows requested than the flow ring holds%s");
+    const long long first_pair = c->pairs_done;
+    int produced = run_frames(c, d, ds, dfs, count, false, 0, nullptr, nullptr);
     CHECK_LAUNCH(c);
-    c->frames_seen++;
-    if (c->frames_seen < 2) return 0;
-    const int T = c->prm.iterations;
-    const float fscale = (float)(1.0 / c->prm.pyr_scale);
-    for (int k = c->nlayers - 1; k >= 0; k--) {
-        Layer& L = c->layer[k];
-        if (k == c->nlayers - 1) rc_launch_update_matrices(c, L.R[prev], L.R[cur], L.M[0], 0, nullptr, 0, 0, 1.f);
-        else {
-            Layer& C = c->layer[k + 1];
-            rc_launch_update_matrices(c, L.R[prev], L.R[cur], L.M[0], 1, C.flow, C.w, C.h, fscale);
-        }
-        int mi = 0;
-        for (int it = 0; it < T; it++) {
-            if (it < T - 1) { rc_launch_update_flow(c, L.M[mi], L.R[prev], L.R[cur], L.M[mi ^ 1], nullptr, nullptr); mi ^= 1; }
-            else rc_launch_update_flow(c, L.M[mi], L.R[prev], L.R[cur], Planes(), L.flow, nullptr);
-        }
+    if (flows && produced > 0) {
+        if (flow_step < (size_t)w * 8) return fail(c, RC_ERR_INVALID, "flow_step too small%s");
+        const bool dev = is_device_ptr(flows);
+        for (int j = 0; j < produced; j++)
+            CUDA_TRY(c, cudaMemcpy2DAsync(reinterpret_cast<char*>(flows) + (size_t)j * flow_stride, flow_step,
+                                          ring_slot(c, first_pair + j), (size_t)w * 8, (size_t)w * 8, h,
+                                          dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+        if (!dev) host = true;
     }
-    CHECK_LAUNCH(c);
-    c->have_flow = true;
-    return 1;
+    if (host) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return produced;
 }
 
 int rc_flow_push(rc_ctx* c, const uint8_t* frame, size_t step, float* flow, size_t flow_step)
 {
-    if (!c) return RC_ERR_INVALID;
-    if (!c->configured) return fail(c, RC_ERR_STATE, "rc_flow_configure has not been called%s");
-    cudaSetDevice(c->device);
-    int produced = flow_push_impl(c, frame, step);
-    if (produced < 0) return produced;
-    bool host = !is_device_ptr(frame);   // the source host buffer must be consumed before we return
-    if (produced == 1 && flow) {
-        if (flow_step < (size_t)c->prm.w * 8) return fail(c, RC_ERR_INVALID, "flow_step too small%s");
-        int rc = copy_out(c, flow, flow_step, c->flow_out, (size_t)c->prm.w * 8, (size_t)c->prm.w * 8, c->prm.h, &host);
-        if (rc) return rc;
-    }
-    if (host) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    return produced;
+    return rc_flow_push_batch(c, frame, step, 0, 1, flow, flow_step, 0);
 }
 
 int rc_farneback(rc_ctx* c, const uint8_t* prev, size_t prev_step, const uint8_t* next, size_t next_step, int w, int h,
@@ -437,9 +562,15 @@ int rc_farneback(rc_ctx* c, const uint8_t* prev, size_t prev_step, const uint8_t
                  double poly_sigma, int flags)
 {
     if (!c) return RC_ERR_INVALID;
-    int rc = rc_flow_configure(c, w, h, pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags);
-    if (rc) return rc;
-    c->frames_seen = 0; c->have_flow = false;
+    int rc;
+    const bool same = c->configured && c->prm.w == w && c->prm.h == h && c->prm.pyr_scale == pyr_scale &&
+                      c->prm.levels == levels && c->prm.winsize == winsize && c->prm.iterations == iterations &&
+                      c->prm.poly_n == poly_n && c->prm.poly_sigma == poly_sigma && c->prm.flags == flags;
+    if (!same) {
+        rc = rc_flow_configure_batch(c, w, h, pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags, 1);
+        if (rc) return rc;
+    }
+    c->frames_seen = 0;      // independent two-frame call: nothing cached is reused
     rc = rc_flow_push(c, prev, prev_step, nullptr, 0);
     if (rc < 0) return rc;
     rc = rc_flow_push(c, next, next_step, flow, flow_step);
@@ -449,10 +580,18 @@ int rc_farneback(rc_ctx* c, const uint8_t* prev, size_t prev_step, const uint8_t
 int rc_flow_device(rc_ctx* c, float** dev_flow, int* w, int* h)
 {
     if (!c || !dev_flow) return RC_ERR_INVALID;
-    if (!c->have_flow) return fail(c, RC_ERR_STATE, "no flow has been computed on this context%s");
-    *dev_flow = c->flow_out;
+    if (!c->pairs_done) return fail(c, RC_ERR_STATE, "no flow has been computed on this context%s");
+    *dev_flow = ring_slot(c, c->pairs_done - 1);
     if (w) *w = c->prm.w;
     if (h) *h = c->prm.h;
+    return RC_OK;
+}
+
+int rc_flow_device_at(rc_ctx* c, int back, float** dev_flow)
+{
+    if (!c || !dev_flow || back < 0) return RC_ERR_INVALID;
+    if (back >= c->pairs_done || back >= c->ring_slots) return fail(c, RC_ERR_STATE, "that flow is no longer resident%s");
+    *dev_flow = ring_slot(c, c->pairs_done - 1 - back);
     return RC_OK;
 }
 
@@ -462,7 +601,7 @@ int rc_hist_reset(rc_ctx* c)
     if (!c) return RC_ERR_INVALID;
     cudaSetDevice(c->device);
     int rc = ensure_aggregate(c); if (rc) return rc;
-    CUDA_TRY(c, cudaMemsetAsync(c->d_hist2d, 0, sizeof(unsigned long long) * RC_HIST_ROWS * RC_HIST_BINS, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_hist2d, 0, sizeof(unsigned long long) * RC_HIST_CELLS, c->stream));
     return RC_OK;
 }
 
@@ -485,7 +624,7 @@ int rc_hist_get(rc_ctx* c, int64_t* hist, int64_t* histsum, int64_t* hist2d, int
     if (!c) return RC_ERR_INVALID;
     cudaSetDevice(c->device);
     int rc = ensure_aggregate(c); if (rc) return rc;
-    int64_t tmp[RC_HIST_ROWS * RC_HIST_BINS];
+    int64_t tmp[RC_HIST_CELLS];
     CUDA_TRY(c, cudaMemcpyAsync(tmp, c->d_hist2d, sizeof tmp, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (hist2d) memcpy(hist2d, tmp, sizeof tmp);
@@ -506,10 +645,10 @@ int rc_hist_add(rc_ctx* c, const int64_t* hist2d)
     if (!c || !hist2d) return RC_ERR_INVALID;
     cudaSetDevice(c->device);
     int rc = ensure_aggregate(c); if (rc) return rc;
-    int64_t tmp[RC_HIST_ROWS * RC_HIST_BINS];
+    int64_t tmp[RC_HIST_CELLS];
     CUDA_TRY(c, cudaMemcpyAsync(tmp, c->d_hist2d, sizeof tmp, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < RC_HIST_ROWS * RC_HIST_BINS; i++) tmp[i] += hist2d[i];
+    for (int i = 0; i < RC_HIST_CELLS; i++) tmp[i] += hist2d[i];
     CUDA_TRY(c, cudaMemcpyAsync(c->d_hist2d, tmp, sizeof tmp, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return RC_OK;
@@ -556,7 +695,7 @@ int rc_thresholds(rc_ctx* c, float* UPPER, float* UPPER2d, float* prop)
     if (!c) return RC_ERR_INVALID;
     cudaSetDevice(c->device);
     int rc = ensure_aggregate(c); if (rc) return rc;
-    rc_launch_thresholds(c, c->d_hist2d, c->d_thr);
+    rc_launch_thresholds_batch(c, c->d_hist2d, nullptr, 0, nullptr, c->d_thr);
     CHECK_LAUNCH(c);
     if (UPPER || UPPER2d || prop) {
         float t[RC_THR_FLOATS];
@@ -578,29 +717,6 @@ int rc_accumulator_reset(rc_ctx* c)
     return RC_OK;
 }
 
-static int classify_impl(rc_ctx* c, const float* d_flow, size_t d_step, int w, int h, float upper, int framecount,
-                         uint8_t* outmask, uint8_t* waveclass, uint8_t* waterclass, bool with_window, bool* host_written)
-{
-    int rc = ensure_aggregate(c); if (rc) return rc;
-    rc = ensure_accumulator(c, w, h); if (rc) return rc;
-    const size_t n = (size_t)w * h;
-    uint8_t* d_mask = outmask ? (is_device_ptr(outmask) ? outmask : c->d_mask) : nullptr;
-    uint8_t* d_wave = waveclass ? (is_device_ptr(waveclass) ? waveclass : c->d_cls) : nullptr;
-    uint8_t* d_water = waterclass ? (is_device_ptr(waterclass) ? waterclass : c->d_cls + n) : nullptr;
-    float* slot = nullptr; float* avg = nullptr;
-    if (with_window && c->win_W > 0 && c->win_w == w && c->win_h == h) {
-        slot = c->d_ring + (size_t)c->win_i * n * 2; avg = c->d_avg;
-        c->win_i = (c->win_i + 1) % c->win_W;
-    }
-    rc_launch_classify(c, d_flow, d_step, w, h, upper, c->d_thr, framecount, c->d_acc, d_mask, d_wave, d_water, slot, avg,
-                       c->win_W);
-    CHECK_LAUNCH(c);
-    if (outmask && d_mask != outmask) { CUDA_TRY(c, cudaMemcpyAsync(outmask, d_mask, n, cudaMemcpyDeviceToHost, c->stream)); *host_written = true; }
-    if (waveclass && d_wave != waveclass) { CUDA_TRY(c, cudaMemcpyAsync(waveclass, d_wave, n, cudaMemcpyDeviceToHost, c->stream)); *host_written = true; }
-    if (waterclass && d_water != waterclass) { CUDA_TRY(c, cudaMemcpyAsync(waterclass, d_water, n, cudaMemcpyDeviceToHost, c->stream)); *host_written = true; }
-    return RC_OK;
-}
-
 int rc_classify_accumulate(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float upper, int framecount,
                            uint8_t* outmask, uint8_t* waveclass, uint8_t* waterclass)
 {
@@ -610,8 +726,17 @@ int rc_classify_accumulate(rc_ctx* c, const float* flow, size_t flow_step, int w
     int rc = stage_flow_in(c, flow, flow_step, w, h, &d_flow, &d_step); if (rc) return rc;
     if (!flow) { w = c->prm.w; h = c->prm.h; }
     bool host = flow && !is_device_ptr(flow);
-    rc = classify_impl(c, d_flow, d_step, w, h, upper, framecount, outmask, waveclass, waterclass, false, &host);
-    if (rc) return rc;
+    rc = ensure_aggregate(c); if (rc) return rc;
+    rc = ensure_accumulator(c, w, h); if (rc) return rc;
+    const size_t n = (size_t)w * h;
+    uint8_t* d_mask = outmask ? (is_device_ptr(outmask) ? outmask : c->d_cls) : nullptr;
+    uint8_t* d_wave = waveclass ? (is_device_ptr(waveclass) ? waveclass : c->d_cls + n) : nullptr;
+    uint8_t* d_water = waterclass ? (is_device_ptr(waterclass) ? waterclass : c->d_cls + 2 * n) : nullptr;
+    rc_launch_classify(c, d_flow, d_step, w, h, upper, c->d_thr, framecount, c->d_acc, d_mask, d_wave, d_water);
+    CHECK_LAUNCH(c);
+    if (outmask && d_mask != outmask) { CUDA_TRY(c, cudaMemcpyAsync(outmask, d_mask, n, cudaMemcpyDeviceToHost, c->stream)); host = true; }
+    if (waveclass && d_wave != waveclass) { CUDA_TRY(c, cudaMemcpyAsync(waveclass, d_wave, n, cudaMemcpyDeviceToHost, c->stream)); host = true; }
+    if (waterclass && d_water != waterclass) { CUDA_TRY(c, cudaMemcpyAsync(waterclass, d_water, n, cudaMemcpyDeviceToHost, c->stream)); host = true; }
     if (host) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return RC_OK;
 }
@@ -631,7 +756,11 @@ int rc_accumulator_get(rc_ctx* c, float* acc_x)
 int rc_accumulator_device(rc_ctx* c, float** dev_acc_x, int* w, int* h)
 {
     if (!c || !dev_acc_x) return RC_ERR_INVALID;
-    if (!c->d_acc) return fail(c, RC_ERR_STATE, "no accumulator yet%s");
+    if (!c->d_acc) {
+        if (!c->configured) return fail(c, RC_ERR_STATE, "no accumulator yet%s");
+        cudaSetDevice(c->device);
+        int rc = ensure_accumulator(c, c->prm.w, c->prm.h); if (rc) return rc;
+    }
     *dev_acc_x = c->d_acc;
     if (w) *w = c->acc_w;
     if (h) *h = c->acc_h;
@@ -644,55 +773,79 @@ int rc_window_configure(rc_ctx* c, int w, int h, int W)
     if (!c) return RC_ERR_INVALID;
     cudaSetDevice(c->device);
     if (w < 1 || h < 1 || W < 0) return fail(c, RC_ERR_INVALID, "bad window geometry%s");
-    if (c->d_ring) { cudaStreamSynchronize(c->stream); cudaFree(c->d_ring); cudaFree(c->d_avg); c->d_ring = c->d_avg = nullptr; }
-    c->win_W = 0; c->win_i = 0;
+    sync_all(c);
+    if (c->d_swin_ring) { cudaFree(c->d_swin_ring); cudaFree(c->d_swin_avg); c->d_swin_ring = c->d_swin_avg = nullptr; }
+    c->swin_W = 0; c->swin_i = 0; c->swin_w = w; c->swin_h = h;
+    // pipeline window (rc_process_frame / rc_process_frames): lives in the flow ring
+    c->win_W = (!c->configured || (c->prm.w == w && c->prm.h == h)) ? W : 0;
+    if (c->configured) {
+        int rc = ensure_flow_ring(c); if (rc) return rc;
+        CUDA_TRY(c, cudaMemsetAsync(c->d_avg, 0, sizeof(float) * 2 * (size_t)c->prm.w * c->prm.h, c->stream));
+    }
     if (W == 0) return RC_OK;
+    // stand-alone window for caller-provided flows (rc_window_update)
     const size_t nb = sizeof(float) * 2 * (size_t)w * h;
-    if (cudaMalloc((void**)&c->d_ring, nb * W) != cudaSuccess || cudaMalloc((void**)&c->d_avg, nb) != cudaSuccess) {
+    if (cudaMalloc((void**)&c->d_swin_ring, nb * W) != cudaSuccess || cudaMalloc((void**)&c->d_swin_avg, nb) != cudaSuccess) {
         cudaGetLastError();
-        if (c->d_ring) cudaFree(c->d_ring);
-        c->d_ring = c->d_avg = nullptr;
+        if (c->d_swin_ring) cudaFree(c->d_swin_ring);
+        c->d_swin_ring = c->d_swin_avg = nullptr;
         return fail(c, RC_ERR_NOMEM, "cudaMalloc failed (window ring)%s");
     }
-    CUDA_TRY(c, cudaMemsetAsync(c->d_ring, 0, nb * W, c->stream));
-    CUDA_TRY(c, cudaMemsetAsync(c->d_avg, 0, nb, c->stream));
-    c->win_W = W; c->win_w = w; c->win_h = h;
+    CUDA_TRY(c, cudaMemsetAsync(c->d_swin_ring, 0, nb * W, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_swin_avg, 0, nb, c->stream));
+    c->swin_W = W;
     return RC_OK;
 }
 
 int rc_window_update(rc_ctx* c, const float* flow, size_t flow_step)
 {
     if (!c) return RC_ERR_INVALID;
-    if (c->win_W <= 0) return fail(c, RC_ERR_STATE, "rc_window_configure has not been called%s");
+    if (c->swin_W <= 0) return fail(c, RC_ERR_STATE, "rc_window_configure has not been called%s");
     cudaSetDevice(c->device);
     const float* d_flow; size_t d_step;
-    int rc = stage_flow_in(c, flow, flow_step, c->win_w, c->win_h, &d_flow, &d_step); if (rc) return rc;
-    if (!flow && (c->prm.w != c->win_w || c->prm.h != c->win_h)) return fail(c, RC_ERR_INVALID, "window / flow size mismatch%s");
-    const size_t n = (size_t)c->win_w * c->win_h;
-    rc_launch_window_update(c, d_flow, d_step, c->win_w, c->win_h, c->d_ring + (size_t)c->win_i * n * 2, c->d_avg, c->win_W);
+    int rc = stage_flow_in(c, flow, flow_step, c->swin_w, c->swin_h, &d_flow, &d_step); if (rc) return rc;
+    if (!flow && (c->prm.w != c->swin_w || c->prm.h != c->swin_h)) return fail(c, RC_ERR_INVALID, "window / flow size mismatch%s");
+    const size_t n = (size_t)c->swin_w * c->swin_h;
+    rc_launch_window_update(c, d_flow, d_step, c->swin_w, c->swin_h, c->d_swin_ring + (size_t)c->swin_i * n * 2,
+                            c->d_swin_avg, c->swin_W);
     CHECK_LAUNCH(c);
-    c->win_i = (c->win_i + 1) % c->win_W;
+    c->swin_i = (c->swin_i + 1) % c->swin_W;
+    c->win_W = 0;            // the caller drives the window explicitly: rc_process_frame(s) leaves it alone
     if (flow && !is_device_ptr(flow)) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return RC_OK;
+}
+
+// The mean maintained by rc_process_frame(s) when the pipeline window is active, otherwise the stand-alone mean
+// driven by rc_window_update.
+static float* active_avg(rc_ctx* c, int* w, int* h)
+{
+    if (c->win_W > 0) { *w = c->prm.w; *h = c->prm.h; return c->d_avg; }
+    if (c->swin_W > 0) { *w = c->swin_w; *h = c->swin_h; return c->d_swin_avg; }
+    return nullptr;
 }
 
 int rc_window_get(rc_ctx* c, float* avg, size_t avg_step)
 {
     if (!c || !avg) return RC_ERR_INVALID;
-    if (c->win_W <= 0) return fail(c, RC_ERR_STATE, "rc_window_configure has not been called%s");
     cudaSetDevice(c->device);
-    bool host = false;
-    int rc = copy_out(c, avg, avg_step, c->d_avg, (size_t)c->win_w * 8, (size_t)c->win_w * 8, c->win_h, &host);
-    if (rc) return rc;
-    if (host) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    int w, h;
+    float* src = active_avg(c, &w, &h);
+    if (!src) return fail(c, RC_ERR_STATE, "rc_window_configure has not been called%s");
+    if (avg_step < (size_t)w * 8) return fail(c, RC_ERR_INVALID, "avg_step too small%s");
+    const bool dev = is_device_ptr(avg);
+    CUDA_TRY(c, cudaMemcpy2DAsync(avg, avg_step, src, (size_t)w * 8, (size_t)w * 8, h,
+                                  dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    if (!dev) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return RC_OK;
 }
 
 int rc_window_device(rc_ctx* c, float** dev_avg)
 {
     if (!c || !dev_avg) return RC_ERR_INVALID;
-    if (c->win_W <= 0) return fail(c, RC_ERR_STATE, "rc_window_configure has not been called%s");
-    *dev_avg = c->d_avg;
+    int w, h;
+    float* src = active_avg(c, &w, &h);
+    if (!src) return fail(c, RC_ERR_STATE, "rc_window_configure has not been called%s");
+    *dev_avg = src;
     return RC_OK;
 }
 
@@ -738,8 +891,7 @@ int rc_advect(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, floa
     const bool hh = home && !is_device_ptr(home);
     float* d_seeds = seeds; float* d_dist = dist; const int32_t* d_home = home;
     if (hs || hd || hh) {
-        // layout of the scratch: seeds | dist | home
-        size_t need = n * 8 + n * 4 + n * 8;
+        size_t need = n * 8 + n * 4 + n * 8;        // seeds | dist | home
         rc = ensure(c, &c->d_tmp2, &c->d_tmp2_cap, need); if (rc) return rc;
         char* base = reinterpret_cast<char*>(c->d_tmp2);
         if (hs) { d_seeds = reinterpret_cast<float*>(base); CUDA_TRY(c, cudaMemcpyAsync(d_seeds, seeds, n * 8, cudaMemcpyHostToDevice, c->stream)); }
@@ -791,41 +943,101 @@ int rc_streakline_step(rc_ctx* c, const float* flow, size_t flow_step, int w, in
     return RC_OK;
 }
 
-// ---- fused per-frame step ------------------------------------------------------------------------------------
-int rc_process_frame(rc_ctx* c, const uint8_t* frame, size_t step, int framecount, uint8_t* outmask,
-                     rc_frame_result* result)
+// ---- fused per-frame / per-batch step -------------------------------------------------------------------------
+int rc_submit_frames(rc_ctx* c, const uint8_t* frames, size_t step, size_t frame_stride, int count, int framecount0,
+                     uint8_t* outmasks, size_t mask_stride, rc_frame_result* results)
 {
     if (!c) return RC_ERR_INVALID;
     if (!c->configured) return fail(c, RC_ERR_STATE, "rc_flow_configure has not been called%s");
+    if (count < 1 || count > c->B) return fail(c, RC_ERR_INVALID, "count must be in [1, max_batch]%s");
     cudaSetDevice(c->device);
-    int rc = ensure_aggregate(c); if (rc) return rc;
-    int produced = flow_push_impl(c, frame, step);
-    if (produced < 0) return produced;
-    bool host = !is_device_ptr(frame);
     const int w = c->prm.w, h = c->prm.h;
-    if (produced) {
-        rc_launch_polar_hist(c, c->flow_out, (size_t)w * 8, w, h, c->d_hist2d);
-        rc_launch_thresholds(c, c->d_hist2d, c->d_thr);
-        CHECK_LAUNCH(c);
-        rc = classify_impl(c, c->flow_out, (size_t)w * 8, w, h, NAN, framecount, outmask, nullptr, nullptr, true, &host);
-        if (rc) return rc;
+    const size_t n = (size_t)w * h;
+    if (!frames || step < (size_t)w || (count > 1 && frame_stride < step * (size_t)(h - 1) + w))
+        return fail(c, RC_ERR_INVALID, "bad frame pointer / step / stride%s");
+    if (outmasks && count > 1 && mask_stride < n) return fail(c, RC_ERR_INVALID, "mask_stride too small%s");
+    int rc = ensure_aggregate(c); if (rc) return rc;
+    rc = ensure_accumulator(c, w, h); if (rc) return rc;
+    const int slot = (int)(c->submitted & 1);
+    rc = finish_slot(c, slot); if (rc) return rc;          // the batch that used this slot two submits ago
+
+    const bool dev_in = is_device_ptr(frames);
+    const uint8_t* d = frames; size_t ds = step, dfs = frame_stride;
+    if (!dev_in) {
+        // H2D on the copy-in stream; it may only overwrite the staging slot once the kernels that read it are done
+        CUDA_TRY(c, cudaStreamWaitEvent(c->s_in, c->ev_compute[slot], 0));
+        if (step == (size_t)w && (count == 1 || frame_stride == n))
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_frames[slot], frames, n * count, cudaMemcpyHostToDevice, c->s_in));
+        else
+            for (int j = 0; j < count; j++)
+                CUDA_TRY(c, cudaMemcpy2DAsync(c->d_frames[slot] + (size_t)j * n, w, frames + (size_t)j * frame_stride, step,
+                                              w, h, cudaMemcpyHostToDevice, c->s_in));
+        CUDA_TRY(c, cudaEventRecord(c->ev_in[slot], c->s_in));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_in[slot], 0));
+        d = c->d_frames[slot]; ds = w; dfs = n;
     }
-    if (result) {
-        memset(result, 0, sizeof *result);
-        result->produced = produced;
-        if (produced) {
-            float t[RC_THR_FLOATS];
-            CUDA_TRY(c, cudaMemcpyAsync(t, c->d_thr, sizeof t, cudaMemcpyDeviceToHost, c->stream));
-            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-            result->UPPER = t[0];
-            memcpy(result->UPPER2d, t + 1, sizeof(float) * RC_HIST_DIRECTIONS);
-            memcpy(result->prop_above_upper, t + 37, sizeof(float) * RC_HIST_DIRECTIONS);
-            memcpy(&result->histsum, t + 74, sizeof(int64_t));
-            host = false;
+    const bool dev_masks = outmasks && is_device_ptr(outmasks);
+    // masks / thresholds of this batch go to staging slot `slot`; its previous D2H must have drained
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_out[slot], 0));
+    const int first_produced = c->frames_seen == 0 ? 1 : 0;
+    const bool direct = dev_masks && (count == 1 || mask_stride == n);
+    uint8_t* d_masks = outmasks ? (direct ? outmasks + (size_t)first_produced * mask_stride : c->d_masks[slot]) : nullptr;
+    int produced = run_frames(c, d, ds, dfs, count, true, framecount0, c->d_thr_batch[slot], d_masks);
+    CHECK_LAUNCH(c);
+    CUDA_TRY(c, cudaEventRecord(c->ev_compute[slot], c->stream));
+    bool host_out = false;
+    if ((outmasks || results) && produced > 0) {
+        CUDA_TRY(c, cudaStreamWaitEvent(c->s_out, c->ev_compute[slot], 0));
+        if (outmasks && !direct) {
+            const cudaMemcpyKind kind = dev_masks ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+            if (count == 1 || mask_stride == n)
+                CUDA_TRY(c, cudaMemcpyAsync(outmasks + (size_t)first_produced * mask_stride, d_masks, n * produced, kind, c->s_out));
+            else
+                for (int j = 0; j < produced; j++)
+                    CUDA_TRY(c, cudaMemcpyAsync(outmasks + (size_t)(first_produced + j) * mask_stride, d_masks + (size_t)j * n, n,
+                                                kind, c->s_out));
+            if (!dev_masks) host_out = true;
+        }
+        if (results) {
+            CUDA_TRY(c, cudaMemcpyAsync(c->h_thr[slot], c->d_thr_batch[slot], sizeof(float) * RC_THR_FLOATS * produced,
+                                        cudaMemcpyDeviceToHost, c->s_out));
+            host_out = true;
         }
     }
-    if (host) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaEventRecord(c->ev_out[slot], c->s_out));
+    if (results || host_out) {
+        c->pending_results[slot] = results; c->pending_count[slot] = count; c->pending_first_produced[slot] = first_produced;
+    }
+    c->submitted++;
     return produced;
+}
+
+int rc_wait(rc_ctx* c)
+{
+    if (!c) return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    const int s0 = (int)(c->submitted & 1);      // oldest first
+    int rc = finish_slot(c, s0); if (rc) return rc;
+    rc = finish_slot(c, s0 ^ 1); if (rc) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_in));
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_out));
+    return RC_OK;
+}
+
+int rc_process_frames(rc_ctx* c, const uint8_t* frames, size_t step, size_t frame_stride, int count, int framecount0,
+                      uint8_t* outmasks, size_t mask_stride, rc_frame_result* results)
+{
+    int produced = rc_submit_frames(c, frames, step, frame_stride, count, framecount0, outmasks, mask_stride, results);
+    if (produced < 0) return produced;
+    const bool host_touch = !is_device_ptr(frames) || results || (outmasks && !is_device_ptr(outmasks));
+    if (host_touch) { int rc = rc_wait(c); if (rc) return rc; }
+    return produced;
+}
+
+int rc_process_frame(rc_ctx* c, const uint8_t* frame, size_t step, int framecount, uint8_t* outmask,
+                     rc_frame_result* result)
+{
+    return rc_process_frames(c, frame, step, 0, 1, framecount, outmask, 0, result);
 }
 
 }  // extern "C"

@@ -2,14 +2,24 @@
 //
 // Functional specification: SURVEY.md Appendix A (the algorithm cv::calcOpticalFlowFarneback runs for the
 // reference's calls at RipCurrents_main/ripcurrents.cpp:215 and main.cpp:264,609,742,961,1119,1481).
-// This file is compiled with -fmad=false: products and sums round separately unless fmaf() is written.
 //
-// HBM layout: every per-pixel coefficient set is PLANAR fp32 (5 planes for the polynomial expansion R and for
-// the structure matrices M) with a row pitch rounded up to 32 floats, so that a warp reads 128 contiguous bytes
-// from each plane; flow is interleaved float2 (CV_32FC2, the output format).
+// Two arithmetic modes (DESIGN.md "Arithmetic"):
+//   strict : every tap, fp64 accumulators where OpenCV has them, products and sums rounded separately
+//            (written with __fmul_rn/__fadd_rn so the compiler cannot contract them);
+//   fast   : (default) fp32 with FMA, Gaussian tails of the expansion kernel below 1e-9 of the centre dropped,
+//            2x2 solve in fp32 with error-free determinants.  Measured as close to cv2 as the strict mode is.
+//
+// HBM layout: per-pixel coefficient sets are PLANAR fp32 (5 planes for the polynomial expansion R and for the
+// structure matrices M), row pitch rounded up to 32 floats, so a warp reads 128 contiguous bytes from each plane;
+// flow is interleaved float2 (CV_32FC2, the output format).  Every array has a leading batch dimension: one
+// launch processes all frame pairs of a batch (blockIdx.z), which is what fills 148 SMs on the small pyramid layers.
 #include "rc_internal.h"
 
 namespace {
+
+template <bool S> __device__ __forceinline__ float fmul(float a, float b) { return S ? __fmul_rn(a, b) : a * b; }
+template <bool S> __device__ __forceinline__ float fadd(float a, float b) { return S ? __fadd_rn(a, b) : a + b; }
+template <bool S> __device__ __forceinline__ float fsub(float a, float b) { return S ? __fsub_rn(a, b) : a - b; }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 __device__ __forceinline__ int reflect101(int p, int len)
@@ -20,7 +30,7 @@ __device__ __forceinline__ int reflect101(int p, int len)
 }
 
 // cv::resize(INTER_LINEAR) source index + weight for destination index d (Appendix A.2)
-__device__ __forceinline__ void resize_coef(int d, int src, int dst, double scale, int& s0, float& f)
+__device__ __forceinline__ void resize_coef(int d, int src, double scale, int& s0, float& f)
 {
     float fx = (float)((d + 0.5) * scale - 0.5);
     int s = (int)floorf(fx);
@@ -28,7 +38,6 @@ __device__ __forceinline__ void resize_coef(int d, int src, int dst, double scal
     if (s < 0) { s = 0; fx = 0.f; }
     if (s >= src - 1) { s = src - 1; fx = 0.f; }
     s0 = s; f = fx;
-    (void)dst;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -36,74 +45,77 @@ __device__ __forceinline__ void resize_coef(int d, int src, int dst, double scal
 // rows then columns, fp32), bilinear resize to (lw, lh).  The blur is evaluated only where the resize samples.
 // pass 1: horizontal blur at the (up to) two source columns each destination column samples, every source row.
 // ---------------------------------------------------------------------------------------------------
-__global__ void pyr_h_kernel(const uint8_t* __restrict__ img, size_t step, int W, int H, int dw, double scale_x,
-                             int two, SmoothCoef sc, float* __restrict__ htmp)
+__global__ void pyr_h_kernel(const uint8_t* __restrict__ img, size_t step, size_t fstride, int W, int H, int dw,
+                             double scale_x, int two, SmoothCoef sc, float* __restrict__ htmp, size_t hstride)
 {
     int X = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (X >= dw || y >= H) return;
+    img += (size_t)blockIdx.z * fstride;
+    htmp += (size_t)blockIdx.z * hstride;
     int sx; float fx;
-    if (two) resize_coef(X, W, dw, scale_x, sx, fx); else sx = X;
+    if (two) resize_coef(X, W, scale_x, sx, fx); else sx = X;
     const uint8_t* row = img + (size_t)y * step;
     const int r = sc.ksize / 2;
     float s0 = 0.f, s1 = 0.f;
     int sx1 = sx + 1 < W ? sx + 1 : W - 1;
     if (sx - r >= 0 && sx1 + r < W) {
         for (int i = 0; i < sc.ksize; i++) {
-            s0 = s0 + sc.k[i] * (float)row[sx + i - r];
-            if (two) s1 = s1 + sc.k[i] * (float)row[sx1 + i - r];
+            s0 = __fadd_rn(s0, __fmul_rn(sc.k[i], (float)row[sx + i - r]));
+            if (two) s1 = __fadd_rn(s1, __fmul_rn(sc.k[i], (float)row[sx1 + i - r]));
         }
     } else {
         for (int i = 0; i < sc.ksize; i++) {
-            s0 = s0 + sc.k[i] * (float)row[reflect101(sx + i - r, W)];
-            if (two) s1 = s1 + sc.k[i] * (float)row[reflect101(sx1 + i - r, W)];
+            s0 = __fadd_rn(s0, __fmul_rn(sc.k[i], (float)row[reflect101(sx + i - r, W)]));
+            if (two) s1 = __fadd_rn(s1, __fmul_rn(sc.k[i], (float)row[reflect101(sx1 + i - r, W)]));
         }
     }
-    if (two) {
-        float2* o = reinterpret_cast<float2*>(htmp) + (size_t)y * dw + X;
-        *o = make_float2(s0, s1);
-    } else {
-        htmp[(size_t)y * dw + X] = s0;
-    }
+    if (two) reinterpret_cast<float2*>(htmp)[(size_t)y * dw + X] = make_float2(s0, s1);
+    else htmp[(size_t)y * dw + X] = s0;
 }
 
 // pass 2: vertical blur at the two source rows each destination row samples, then the bilinear combination.
-__global__ void pyr_v_kernel(const float* __restrict__ htmp, int W, int H, int dw, int dh, double scale_x,
-                             double scale_y, int two, SmoothCoef sc, float* __restrict__ out, int pitch)
+__global__ void pyr_v_kernel(const float* __restrict__ htmp, size_t hstride, int W, int H, int dw, int dh,
+                             double scale_x, double scale_y, int two, SmoothCoef sc, float* __restrict__ out, int pitch,
+                             size_t ostride)
 {
     int X = blockIdx.x * blockDim.x + threadIdx.x;
     int Y = blockIdx.y * blockDim.y + threadIdx.y;
     if (X >= dw || Y >= dh) return;
+    htmp += (size_t)blockIdx.z * hstride;
+    out += (size_t)blockIdx.z * ostride;
     const int r = sc.ksize / 2;
     if (!two) {
         float s = 0.f;
-        for (int j = 0; j < sc.ksize; j++) s = s + sc.k[j] * htmp[(size_t)reflect101(Y + j - r, H) * dw + X];
+        for (int j = 0; j < sc.ksize; j++)
+            s = __fadd_rn(s, __fmul_rn(sc.k[j], htmp[(size_t)reflect101(Y + j - r, H) * dw + X]));
         out[(size_t)Y * pitch + X] = s;
         return;
     }
     int sx, sy; float fx, fy;
-    resize_coef(X, W, dw, scale_x, sx, fx);
-    resize_coef(Y, H, dh, scale_y, sy, fy);
+    resize_coef(X, W, scale_x, sx, fx);
+    resize_coef(Y, H, scale_y, sy, fy);
     int sy1 = sy + 1 < H ? sy + 1 : H - 1;
     const float2* t = reinterpret_cast<const float2*>(htmp);
     float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
     for (int j = 0; j < sc.ksize; j++) {
         float2 a = t[(size_t)reflect101(sy + j - r, H) * dw + X];
         float2 b = t[(size_t)reflect101(sy1 + j - r, H) * dw + X];
-        b00 = b00 + sc.k[j] * a.x; b01 = b01 + sc.k[j] * a.y;
-        b10 = b10 + sc.k[j] * b.x; b11 = b11 + sc.k[j] * b.y;
+        b00 = __fadd_rn(b00, __fmul_rn(sc.k[j], a.x)); b01 = __fadd_rn(b01, __fmul_rn(sc.k[j], a.y));
+        b10 = __fadd_rn(b10, __fmul_rn(sc.k[j], b.x)); b11 = __fadd_rn(b11, __fmul_rn(sc.k[j], b.y));
     }
-    float top = b00 * (1.f - fx) + b01 * fx;
-    float bot = b10 * (1.f - fx) + b11 * fx;
-    out[(size_t)Y * pitch + X] = top * (1.f - fy) + bot * fy;
+    float top = __fadd_rn(__fmul_rn(b00, 1.f - fx), __fmul_rn(b01, fx));
+    float bot = __fadd_rn(__fmul_rn(b10, 1.f - fx), __fmul_rn(b11, fx));
+    out[(size_t)Y * pitch + X] = __fadd_rn(__fmul_rn(top, 1.f - fy), __fmul_rn(bot, fy));
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Polynomial expansion (Appendix A.3), reference tile kernel: vertical pass fp32 -> shared memory,
-// horizontal pass with fp64 accumulators, replicate borders.
+// Polynomial expansion (Appendix A.3), STRICT tile kernel: vertical pass fp32 -> shared memory,
+// horizontal pass with fp64 accumulators, replicate borders, every tap, no contraction.
 // ---------------------------------------------------------------------------------------------------
 template <int TX, int TY>
-__global__ void polyexp_ref_kernel(const float* __restrict__ I, int w, int h, int pitch, Planes R, PolyCoef pc)
+__global__ void polyexp_strict_kernel(const float* __restrict__ I, size_t istride, int w, int h, int pitch,
+                                      float* __restrict__ R, size_t plane, int first_slot, int nslots, PolyCoef pc)
 {
     extern __shared__ float sm[];
     const int n = pc.n;
@@ -112,6 +124,8 @@ __global__ void polyexp_ref_kernel(const float* __restrict__ I, int w, int h, in
     float* sr = sm + (TY + 2 * n) * SW;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const int tid = threadIdx.x, nt = blockDim.x;
+    I += (size_t)blockIdx.z * istride;
+    R += (size_t)((first_slot + blockIdx.z) % nslots) * 5 * plane;
 
     for (int idx = tid; idx < (TY + 2 * n) * SW; idx += nt) {
         int r = idx / SW, c = idx - r * SW;
@@ -122,13 +136,13 @@ __global__ void polyexp_ref_kernel(const float* __restrict__ I, int w, int h, in
     for (int idx = tid; idx < TY * SW; idx += nt) {
         int r = idx / SW, c = idx - r * SW;
         const float* col = sI + (r + n) * SW + c;
-        float r0 = col[0] * pc.g[0], r1 = 0.f, r2 = 0.f;
+        float r0 = __fmul_rn(col[0], pc.g[0]), r1 = 0.f, r2 = 0.f;
         for (int k = 1; k <= n; k++) {
             float up = col[-k * SW], dn = col[k * SW];
-            float p = up + dn;
-            r0 = r0 + pc.g[k] * p;
-            r1 = r1 + pc.xg[k] * (dn - up);
-            r2 = r2 + pc.xxg[k] * p;
+            float p = __fadd_rn(up, dn);
+            r0 = __fadd_rn(r0, __fmul_rn(pc.g[k], p));
+            r1 = __fadd_rn(r1, __fmul_rn(pc.xg[k], __fsub_rn(dn, up)));
+            r2 = __fadd_rn(r2, __fmul_rn(pc.xxg[k], p));
         }
         sr[idx] = r0; sr[TY * SW + idx] = r1; sr[2 * TY * SW + idx] = r2;
     }
@@ -140,169 +154,509 @@ __global__ void polyexp_ref_kernel(const float* __restrict__ I, int w, int h, in
         const float* q0 = sr + r * SW + c + n;
         const float* q1 = q0 + TY * SW;
         const float* q2 = q1 + TY * SW;
-        double b1 = q0[0] * pc.g[0], b2 = 0, b3 = q1[0] * pc.g[0], b4 = 0, b5 = q2[0] * pc.g[0], b6 = 0;
+        double b1 = __fmul_rn(q0[0], pc.g[0]), b2 = 0, b3 = __fmul_rn(q1[0], pc.g[0]), b4 = 0,
+               b5 = __fmul_rn(q2[0], pc.g[0]), b6 = 0;
         for (int k = 1; k <= n; k++) {
-            double tg = q0[k] + q0[-k];
-            b1 += tg * pc.g[k];
-            b4 += tg * pc.xxg[k];
-            b2 += (q0[k] - q0[-k]) * pc.xg[k];
-            b3 += (q1[k] + q1[-k]) * pc.g[k];
-            b6 += (q1[k] - q1[-k]) * pc.xg[k];
-            b5 += (q2[k] + q2[-k]) * pc.g[k];
+            double tg = __fadd_rn(q0[k], q0[-k]);
+            b1 = __dadd_rn(b1, __dmul_rn(tg, (double)pc.g[k]));
+            b4 = __dadd_rn(b4, __dmul_rn(tg, (double)pc.xxg[k]));
+            b2 = __dadd_rn(b2, __dmul_rn((double)__fsub_rn(q0[k], q0[-k]), (double)pc.xg[k]));
+            b3 = __dadd_rn(b3, __dmul_rn((double)__fadd_rn(q1[k], q1[-k]), (double)pc.g[k]));
+            b6 = __dadd_rn(b6, __dmul_rn((double)__fsub_rn(q1[k], q1[-k]), (double)pc.xg[k]));
+            b5 = __dadd_rn(b5, __dmul_rn((double)__fadd_rn(q2[k], q2[-k]), (double)pc.g[k]));
         }
-        size_t o = (size_t)y * R.pitch + x;
-        R.plane(0)[o] = (float)(b3 * pc.ig11);
-        R.plane(1)[o] = (float)(b2 * pc.ig11);
-        R.plane(2)[o] = (float)(b1 * pc.ig03 + b5 * pc.ig33);
-        R.plane(3)[o] = (float)(b1 * pc.ig03 + b4 * pc.ig33);
-        R.plane(4)[o] = (float)(b6 * pc.ig55);
+        size_t o = (size_t)y * pitch + x;
+        R[o] = (float)__dmul_rn(b3, pc.ig11);
+        R[plane + o] = (float)__dmul_rn(b2, pc.ig11);
+        R[2 * plane + o] = (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b5, pc.ig33));
+        R[3 * plane + o] = (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b4, pc.ig33));
+        R[4 * plane + o] = (float)__dmul_rn(b6, pc.ig55);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// updateMatrices for one pixel (Appendix A.5).  R0/R1/M planar.
+// Polynomial expansion, FAST kernel.  NP = evaluated taps per side (multiple of 4; weights beyond poly_n are 0).
+// CTA tile: TX = 128 - 2*NP outputs wide, 32 rows.  Shared row width is exactly 128 floats.
+//  phase V: thread = (column, 16-row segment): its 16 + 2*NP input values come straight from global memory into
+//           registers (coalesced 128 B per warp and row, all loads independent), the three vertical sums of each
+//           of its rows are formed with FMAs and stored to shared memory.
+//  phase H: thread = (row, 4 adjacent outputs): its (4 + 2*NP)-wide window of each vertical sum is read with
+//           conflict-free 16-byte shared loads; six symmetric/antisymmetric FMA chains; 16-byte plane stores.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void update_matrices_px(int x, int y, float dx, float dy, int w, int h, const Planes& R0,
-                                                   const Planes& R1, const Planes& M)
+struct PolyCoefF {
+    float g[RC_MAX_POLY_N + 1], xg[RC_MAX_POLY_N + 1], xxg[RC_MAX_POLY_N + 1];
+    float ig11, ig03, ig33, ig55;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(256)
+polyexp_fast_kernel(const float* __restrict__ I, size_t istride, int w, int h, int pitch, float* __restrict__ R,
+                    size_t plane, int first_slot, int nslots, PolyCoefF pc)
 {
-    const size_t p = (size_t)y * R0.pitch + x;
-    float fx = (float)x + dx, fy = (float)y + dy;
+    constexpr int TX = 128 - 2 * NP, TY = 32, SW = 128, VB = 16, WIN = VB + 2 * NP;
+    __shared__ __align__(16) float sr[3][TY][SW];
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int tid = threadIdx.x;
+    I += (size_t)blockIdx.z * istride;
+    R += (size_t)((first_slot + blockIdx.z) % nslots) * 5 * plane;
+
+    {   // ---- phase V
+        const int col = tid & 127, seg = tid >> 7;
+        const int gx = clampi(x0 - NP + col, 0, w - 1);
+        const int ybase = y0 + seg * VB - NP;
+        float win[WIN];
+#pragma unroll
+        for (int j = 0; j < WIN; j++) win[j] = __ldg(I + (size_t)clampi(ybase + j, 0, h - 1) * pitch + gx);
+#pragma unroll
+        for (int i = 0; i < VB; i++) {
+            float r0 = win[i + NP] * pc.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= NP; k++) {
+                float up = win[i + NP - k], dn = win[i + NP + k];
+                float p = up + dn;
+                r0 = fmaf(pc.g[k], p, r0);
+                r1 = fmaf(pc.xg[k], dn - up, r1);
+                r2 = fmaf(pc.xxg[k], p, r2);
+            }
+            sr[0][seg * VB + i][col] = r0; sr[1][seg * VB + i][col] = r1; sr[2][seg * VB + i][col] = r2;
+        }
+    }
+    __syncthreads();
+    {   // ---- phase H
+        constexpr int GPR = TX / 4;            // 4-wide groups per row
+        constexpr int NW = 4 + 2 * NP;         // window width
+        for (int it = tid; it < TY * GPR; it += 256) {
+            const int row = it / GPR, xg4 = it - row * GPR;
+            const int x = x0 + 4 * xg4, y = y0 + row;
+            if (x >= w || y >= h) continue;
+            float wv[NW];
+            float b1[4], b2[4], b4[4], t1[4];
+            // r0 window: b1 (g), b2 (xg, antisymmetric), b4 (xxg)
+#pragma unroll
+            for (int j = 0; j < NW / 4; j++)
+                *reinterpret_cast<float4*>(wv + 4 * j) = *reinterpret_cast<const float4*>(&sr[0][row][4 * xg4 + 4 * j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float a1 = wv[NP + i] * pc.g[0], a2 = 0.f, a4 = 0.f;
+#pragma unroll
+                for (int k = 1; k <= NP; k++) {
+                    float p = wv[NP + i + k], m = wv[NP + i - k];
+                    float tg = p + m;
+                    a1 = fmaf(tg, pc.g[k], a1);
+                    a4 = fmaf(tg, pc.xxg[k], a4);
+                    a2 = fmaf(p - m, pc.xg[k], a2);
+                }
+                b1[i] = a1; b2[i] = a2; b4[i] = a4;
+            }
+            float o1[4], o3[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                o1[i] = b2[i] * pc.ig11;
+                t1[i] = b1[i] * pc.ig03;
+                o3[i] = fmaf(b4[i], pc.ig33, t1[i]);
+            }
+            // r2 window: b5 (g)
+            float o2[4];
+#pragma unroll
+            for (int j = 0; j < NW / 4; j++)
+                *reinterpret_cast<float4*>(wv + 4 * j) = *reinterpret_cast<const float4*>(&sr[2][row][4 * xg4 + 4 * j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float a5 = wv[NP + i] * pc.g[0];
+#pragma unroll
+                for (int k = 1; k <= NP; k++) a5 = fmaf(wv[NP + i + k] + wv[NP + i - k], pc.g[k], a5);
+                o2[i] = fmaf(a5, pc.ig33, t1[i]);
+            }
+            // r1 window: b3 (g), b6 (xg, antisymmetric)
+            float o0[4], o4[4];
+#pragma unroll
+            for (int j = 0; j < NW / 4; j++)
+                *reinterpret_cast<float4*>(wv + 4 * j) = *reinterpret_cast<const float4*>(&sr[1][row][4 * xg4 + 4 * j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float a3 = wv[NP + i] * pc.g[0], a6 = 0.f;
+#pragma unroll
+                for (int k = 1; k <= NP; k++) {
+                    float p = wv[NP + i + k], m = wv[NP + i - k];
+                    a3 = fmaf(p + m, pc.g[k], a3);
+                    a6 = fmaf(p - m, pc.xg[k], a6);
+                }
+                o0[i] = a3 * pc.ig11; o4[i] = a6 * pc.ig55;
+            }
+            const size_t o = (size_t)y * pitch + x;
+            if (x + 3 < w) {
+                *reinterpret_cast<float4*>(R + o) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+                *reinterpret_cast<float4*>(R + plane + o) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+                *reinterpret_cast<float4*>(R + 2 * plane + o) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+                *reinterpret_cast<float4*>(R + 3 * plane + o) = make_float4(o3[0], o3[1], o3[2], o3[3]);
+                *reinterpret_cast<float4*>(R + 4 * plane + o) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (x + i < w) {
+                        R[o + i] = o0[i]; R[plane + o + i] = o1[i]; R[2 * plane + o + i] = o2[i];
+                        R[3 * plane + o + i] = o3[i]; R[4 * plane + o + i] = o4[i];
+                    }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// updateMatrices for one pixel (Appendix A.5).  R0/R1 = 5 planes each.  Result -> m[5].
+// ---------------------------------------------------------------------------------------------------
+template <bool S>
+__device__ __forceinline__ void update_matrices_core(int x, int y, float dx, float dy, int w, int h,
+                                                     const float* __restrict__ R0, const float* __restrict__ R1,
+                                                     size_t plane, int pitch, float m[5])
+{
+    const size_t p = (size_t)y * pitch + x;
+    float fx = fadd<S>((float)x, dx), fy = fadd<S>((float)y, dy);
     int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
-    fx -= (float)x1; fy -= (float)y1;
-    const float r0_0 = R0.plane(0)[p], r0_1 = R0.plane(1)[p], r0_2 = R0.plane(2)[p], r0_3 = R0.plane(3)[p],
-                r0_4 = R0.plane(4)[p];
+    fx = fsub<S>(fx, (float)x1); fy = fsub<S>(fy, (float)y1);
+    const float r0_0 = __ldg(R0 + p), r0_1 = __ldg(R0 + plane + p), r0_2 = __ldg(R0 + 2 * plane + p),
+                r0_3 = __ldg(R0 + 3 * plane + p), r0_4 = __ldg(R0 + 4 * plane + p);
     float r2, r3, r4, r5, r6;
     if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        const size_t q = (size_t)y1 * R1.pitch + x1, qd = q + R1.pitch;
-        const float* c0 = R1.plane(0); const float* c1 = R1.plane(1); const float* c2 = R1.plane(2);
-        const float* c3 = R1.plane(3); const float* c4 = R1.plane(4);
-        r2 = a00 * __ldg(c0 + q) + a01 * __ldg(c0 + q + 1) + a10 * __ldg(c0 + qd) + a11 * __ldg(c0 + qd + 1);
-        r3 = a00 * __ldg(c1 + q) + a01 * __ldg(c1 + q + 1) + a10 * __ldg(c1 + qd) + a11 * __ldg(c1 + qd + 1);
-        r4 = a00 * __ldg(c2 + q) + a01 * __ldg(c2 + q + 1) + a10 * __ldg(c2 + qd) + a11 * __ldg(c2 + qd + 1);
-        r5 = a00 * __ldg(c3 + q) + a01 * __ldg(c3 + q + 1) + a10 * __ldg(c3 + qd) + a11 * __ldg(c3 + qd + 1);
-        r6 = a00 * __ldg(c4 + q) + a01 * __ldg(c4 + q + 1) + a10 * __ldg(c4 + qd) + a11 * __ldg(c4 + qd + 1);
-        r4 = (r0_2 + r4) * 0.5f;
-        r5 = (r0_3 + r5) * 0.5f;
-        r6 = (r0_4 + r6) * 0.25f;
+        const float a00 = fmul<S>(1.f - fx, 1.f - fy), a01 = fmul<S>(fx, 1.f - fy), a10 = fmul<S>(1.f - fx, fy),
+                    a11 = fmul<S>(fx, fy);
+        const size_t q = (size_t)y1 * pitch + x1, qd = q + pitch;
+        float v[5];
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            const float* pl = R1 + c * plane;
+            float t = fmul<S>(a00, __ldg(pl + q));
+            t = fadd<S>(t, fmul<S>(a01, __ldg(pl + q + 1)));
+            t = fadd<S>(t, fmul<S>(a10, __ldg(pl + qd)));
+            t = fadd<S>(t, fmul<S>(a11, __ldg(pl + qd + 1)));
+            v[c] = t;
+        }
+        r2 = v[0]; r3 = v[1];
+        r4 = fmul<S>(fadd<S>(r0_2, v[2]), 0.5f);
+        r5 = fmul<S>(fadd<S>(r0_3, v[3]), 0.5f);
+        r6 = fmul<S>(fadd<S>(r0_4, v[4]), 0.25f);
     } else {
         r2 = r3 = 0.f;
-        r4 = r0_2; r5 = r0_3; r6 = r0_4 * 0.5f;
+        r4 = r0_2; r5 = r0_3; r6 = fmul<S>(r0_4, 0.5f);
     }
-    r2 = (r0_0 - r2) * 0.5f;
-    r3 = (r0_1 - r3) * 0.5f;
-    r2 = r2 + (r4 * dy + r6 * dx);
-    r3 = r3 + (r6 * dy + r5 * dx);
+    r2 = fmul<S>(fsub<S>(r0_0, r2), 0.5f);
+    r3 = fmul<S>(fsub<S>(r0_1, r3), 0.5f);
+    r2 = fadd<S>(r2, fadd<S>(fmul<S>(r4, dy), fmul<S>(r6, dx)));
+    r3 = fadd<S>(r3, fadd<S>(fmul<S>(r6, dy), fmul<S>(r5, dx)));
     if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
         const float border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
-        float scale = (x < 5 ? border[x] : 1.f) * (x >= w - 5 ? border[w - x - 1] : 1.f) *
-                      (y < 5 ? border[y] : 1.f) * (y >= h - 5 ? border[h - y - 1] : 1.f);
-        r2 *= scale; r3 *= scale; r4 *= scale; r5 *= scale; r6 *= scale;
+        float scale = __fmul_rn(__fmul_rn(__fmul_rn(x < 5 ? border[x] : 1.f, x >= w - 5 ? border[w - x - 1] : 1.f),
+                                          y < 5 ? border[y] : 1.f), y >= h - 5 ? border[h - y - 1] : 1.f);
+        r2 = __fmul_rn(r2, scale); r3 = __fmul_rn(r3, scale); r4 = __fmul_rn(r4, scale);
+        r5 = __fmul_rn(r5, scale); r6 = __fmul_rn(r6, scale);
     }
-    const size_t o = (size_t)y * M.pitch + x;
-    M.plane(0)[o] = r4 * r4 + r6 * r6;
-    M.plane(1)[o] = (r4 + r5) * r6;
-    M.plane(2)[o] = r5 * r5 + r6 * r6;
-    M.plane(3)[o] = r4 * r2 + r6 * r3;
-    M.plane(4)[o] = r6 * r2 + r5 * r3;
+    m[0] = fadd<S>(fmul<S>(r4, r4), fmul<S>(r6, r6));
+    m[1] = fmul<S>(fadd<S>(r4, r5), r6);
+    m[2] = fadd<S>(fmul<S>(r5, r5), fmul<S>(r6, r6));
+    m[3] = fadd<S>(fmul<S>(r4, r2), fmul<S>(r6, r3));
+    m[4] = fadd<S>(fmul<S>(r6, r2), fmul<S>(r5, r3));
 }
 
-// updateMatrices with the flow initialisation of Appendix A.4 fused in: the upsampled flow is never stored
-// (the next flow is a function of the blurred M only).
-__global__ void update_matrices_kernel(Planes R0, Planes R1, Planes M, int flow_mode, const float* __restrict__ flow,
-                                       int cw, int ch, double sx_scale, double sy_scale, float flow_scale)
+// Flow initialisation of Appendix A.4 at pixel (x, y) of a w x h layer from the coarser layer's flow.
+template <bool S>
+__device__ __forceinline__ float2 upsample_flow(const float* __restrict__ coarse, int cw, int ch, int x, int y,
+                                                double sxs, double sys, float fscale)
 {
-    const int w = R0.w, h = R0.h;
+    int sx, sy; float fx, fy;
+    resize_coef(x, cw, sxs, sx, fx);
+    resize_coef(y, ch, sys, sy, fy);
+    int sx1 = sx + 1 < cw ? sx + 1 : cw - 1, sy1 = sy + 1 < ch ? sy + 1 : ch - 1;
+    const float2* cf = reinterpret_cast<const float2*>(coarse);
+    float2 a = __ldg(cf + (size_t)sy * cw + sx), b = __ldg(cf + (size_t)sy * cw + sx1);
+    float2 c = __ldg(cf + (size_t)sy1 * cw + sx), d = __ldg(cf + (size_t)sy1 * cw + sx1);
+    float tx = fadd<S>(fmul<S>(a.x, 1.f - fx), fmul<S>(b.x, fx)), ty = fadd<S>(fmul<S>(a.y, 1.f - fx), fmul<S>(b.y, fx));
+    float bx = fadd<S>(fmul<S>(c.x, 1.f - fx), fmul<S>(d.x, fx)), by = fadd<S>(fmul<S>(c.y, 1.f - fx), fmul<S>(d.y, fx));
+    float2 r;
+    r.x = fmul<S>(fadd<S>(fmul<S>(tx, 1.f - fy), fmul<S>(bx, fy)), fscale);
+    r.y = fmul<S>(fadd<S>(fmul<S>(ty, 1.f - fy), fmul<S>(by, fy)), fscale);
+    return r;
+}
+
+// arguments shared by the per-layer flow kernels
+struct FlowArgs {
+    const float* R; size_t plane; int pitch; int w, h; int nslots, prev_slot;
+    const float* coarse; int cw, ch; size_t coarse_stride; double sxs, sys; float fscale;   // coarse == null: zero flow
+    float* M; size_t m_stride;             // unfused path: [B][2][5 planes]
+    float* flow; size_t flow_stride;       // this layer's flow (layers >= 1), or null when flow_dst is used
+    float* flow_dst[RC_MAX_BATCH];         // layer 0: per-pair destination (flow ring slots)
+    unsigned int* hist_delta;              // layer 0: per-pair histogram counts or null
+    WinCoef win;
+    __device__ __forceinline__ const float* R0(int j) const { return R + (size_t)((prev_slot + j) % nslots) * 5 * plane; }
+    __device__ __forceinline__ const float* R1(int j) const { return R + (size_t)((prev_slot + j + 1) % nslots) * 5 * plane; }
+    __device__ __forceinline__ float* out(int j) const { return flow ? flow + (size_t)j * flow_stride : flow_dst[j]; }
+};
+
+// ---- unfused path (strict mode, or windows too large for the fused kernel) -----------------------------------
+template <bool S>
+__global__ void update_matrices_kernel(FlowArgs a, int mi)
+{
+    const int w = a.w, h = a.h, j = blockIdx.z;
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
-    float dx = 0.f, dy = 0.f;
-    if (flow_mode == 2) {
-        float2 f = reinterpret_cast<const float2*>(flow)[(size_t)y * w + x];
-        dx = f.x; dy = f.y;
-    } else if (flow_mode == 1) {
-        int sx, sy; float fx, fy;
-        resize_coef(x, cw, w, sx_scale, sx, fx);
-        resize_coef(y, ch, h, sy_scale, sy, fy);
-        int sx1 = sx + 1 < cw ? sx + 1 : cw - 1, sy1 = sy + 1 < ch ? sy + 1 : ch - 1;
-        const float2* cf = reinterpret_cast<const float2*>(flow);
-        float2 a = __ldg(cf + (size_t)sy * cw + sx), b = __ldg(cf + (size_t)sy * cw + sx1);
-        float2 c = __ldg(cf + (size_t)sy1 * cw + sx), d = __ldg(cf + (size_t)sy1 * cw + sx1);
-        float tx = a.x * (1.f - fx) + b.x * fx, ty = a.y * (1.f - fx) + b.y * fx;
-        float bx = c.x * (1.f - fx) + d.x * fx, by = c.y * (1.f - fx) + d.y * fx;
-        dx = (tx * (1.f - fy) + bx * fy) * flow_scale;
-        dy = (ty * (1.f - fy) + by * fy) * flow_scale;
+    float2 f = make_float2(0.f, 0.f);
+    if (a.coarse) f = upsample_flow<S>(a.coarse + (size_t)j * a.coarse_stride, a.cw, a.ch, x, y, a.sxs, a.sys, a.fscale);
+    float m[5];
+    update_matrices_core<S>(x, y, f.x, f.y, w, h, a.R0(j), a.R1(j), a.plane, a.pitch, m);
+    float* M = a.M + (size_t)j * a.m_stride + (size_t)mi * 5 * a.plane;
+    const size_t o = (size_t)y * a.pitch + x;
+#pragma unroll
+    for (int c = 0; c < 5; c++) M[c * a.plane + o] = m[c];
+}
+
+__device__ __forceinline__ float2 solve_strict(double g11, double g12, double g22, double h1, double h2)
+{
+    double det = __dadd_rn(__dsub_rn(__dmul_rn(g11, g22), __dmul_rn(g12, g12)), 1e-3);
+    double idet = __ddiv_rn(1.0, det);
+    return make_float2((float)__dmul_rn(__dsub_rn(__dmul_rn(g11, h2), __dmul_rn(g12, h1)), idet),
+                       (float)__dmul_rn(__dsub_rn(__dmul_rn(g22, h1), __dmul_rn(g12, h2)), idet));
+}
+
+// a*b - c*d with one rounding error (Kahan): exact product error of c*d recovered with an FMA
+__device__ __forceinline__ float det2(float a, float b, float c, float d)
+{
+    float w = c * d;
+    float e = fmaf(c, d, -w);
+    float f = fmaf(a, b, -w);
+    return f - e;
+}
+
+__device__ __forceinline__ float2 solve_fast(float g11, float g12, float g22, float h1, float h2)
+{
+    float idet = 1.f / (det2(g11, g22, g12, g12) + 1e-3f);
+    return make_float2(det2(g11, h2, g12, h1) * idet, det2(g22, h1, g12, h2) * idet);
+}
+
+// one updateFlow iteration, per-pixel reference form: blur(M[mi]) -> solve -> (fused updateMatrices -> M[mi^1] | flow)
+template <bool FUSE>
+__global__ void update_flow_strict_kernel(FlowArgs a, int mi)
+{
+    const int w = a.w, h = a.h, j = blockIdx.z, m = a.win.m;
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const float* Min = a.M + (size_t)j * a.m_stride + (size_t)mi * 5 * a.plane;
+    float2 f;
+    if (!a.win.gaussian) {
+        double s[5] = {0, 0, 0, 0, 0};
+        for (int i = -m; i <= m; i++) {
+            int xx = clampi(x + i, 0, w - 1);
+            double v[5] = {0, 0, 0, 0, 0};
+            for (int jj = -m; jj <= m; jj++) {
+                size_t o = (size_t)clampi(y + jj, 0, h - 1) * a.pitch + xx;
+#pragma unroll
+                for (int c = 0; c < 5; c++) v[c] = __dadd_rn(v[c], (double)__ldg(Min + c * a.plane + o));
+            }
+#pragma unroll
+            for (int c = 0; c < 5; c++) s[c] = __dadd_rn(s[c], v[c]);
+        }
+        const double sc = a.win.post_scale_d;
+        f = solve_strict(__dmul_rn(s[0], sc), __dmul_rn(s[1], sc), __dmul_rn(s[2], sc), __dmul_rn(s[3], sc),
+                         __dmul_rn(s[4], sc));
+    } else {
+        auto vcol = [&](int xx, float* v) {
+            size_t o = (size_t)y * a.pitch + xx;
+#pragma unroll
+            for (int c = 0; c < 5; c++) v[c] = __fmul_rn(__ldg(Min + c * a.plane + o), a.win.k[0]);
+            for (int jj = 1; jj <= m; jj++) {
+                size_t ou = (size_t)clampi(y - jj, 0, h - 1) * a.pitch + xx;
+                size_t od = (size_t)clampi(y + jj, 0, h - 1) * a.pitch + xx;
+#pragma unroll
+                for (int c = 0; c < 5; c++)
+                    v[c] = __fadd_rn(v[c], __fmul_rn(__fadd_rn(__ldg(Min + c * a.plane + od), __ldg(Min + c * a.plane + ou)),
+                                                     a.win.k[jj]));
+            }
+        };
+        float hs[5], v0[5], va[5], vb[5];
+        vcol(x, v0);
+#pragma unroll
+        for (int c = 0; c < 5; c++) hs[c] = __fmul_rn(v0[c], a.win.k[0]);
+        for (int i = 1; i <= m; i++) {
+            vcol(clampi(x - i, 0, w - 1), va);
+            vcol(clampi(x + i, 0, w - 1), vb);
+#pragma unroll
+            for (int c = 0; c < 5; c++) hs[c] = __fadd_rn(hs[c], __fmul_rn(a.win.k[i], __fadd_rn(va[c], vb[c])));
+        }
+        f = solve_strict(hs[0], hs[1], hs[2], hs[3], hs[4]);
     }
-    update_matrices_px(x, y, dx, dy, w, h, R0, R1, M);
+    if (FUSE) {
+        float mm[5];
+        update_matrices_core<true>(x, y, f.x, f.y, w, h, a.R0(j), a.R1(j), a.plane, a.pitch, mm);
+        float* Mo = a.M + (size_t)j * a.m_stride + (size_t)(mi ^ 1) * 5 * a.plane;
+        const size_t o = (size_t)y * a.pitch + x;
+#pragma unroll
+        for (int c = 0; c < 5; c++) Mo[c * a.plane + o] = mm[c];
+    } else {
+        reinterpret_cast<float2*>(a.out(j))[(size_t)y * w + x] = f;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// updateFlow (Appendix A.6 box / A.7 Gaussian), reference per-pixel kernels.
+// FAST path, 3x3 window (winsize 2 or 3): ONE kernel per pyramid layer.  A 32x32 output tile carries a halo of
+// NT pixels; the structure matrices M never leave shared memory:
+//   stage 0      M0 = updateMatrices(initial flow) on (32+2NT)^2 cells (out-of-image cells = clamped pixel: replicate)
+//   iteration i  flow_i = solve(blur3x3(M)) on the region shrunk by 1; if not last: M = updateMatrices(flow_i)
+//   last         flow -> HBM (+ the frame's direction/speed histogram on layer 0)
+// HBM traffic per pixel: R0 (20 B) + R1 gather (~20 B) + coarse flow (2 B) + flow out (8 B) instead of
+// 62 + 80 (NT-1) + 28 B for the per-iteration schedule.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 solve2x2(double g11, double g12, double g22, double h1, double h2)
+__device__ __forceinline__ int hist_key_fast(float dx, float dy);   // aggregate.cu twin, defined below
+
+template <int NT>
+__global__ void __launch_bounds__(256)
+flow_layer_kernel(FlowArgs a)
 {
-    double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
-    return make_float2((float)((g11 * h2 - g12 * h1) * idet), (float)((g22 * h1 - g12 * h2) * idet));
+    constexpr int T = 32, HALO = NT, RS = T + 2 * HALO, RP = RS + 1;
+    constexpr int FS = T + 2 * (HALO - 1);                 // side of the largest intermediate flow region
+    __shared__ float sM[5][RS][RP];
+    __shared__ float2 sF[NT > 1 ? FS * FS : 1];
+    __shared__ unsigned int sH[RC_HIST_CELLS];
+    const int w = a.w, h = a.h, j = blockIdx.z, tid = threadIdx.x;
+    const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
+    const float* R0 = a.R0(j);
+    const float* R1 = a.R1(j);
+    const bool do_hist = a.hist_delta != nullptr;
+    if (do_hist) for (int i = tid; i < RC_HIST_CELLS; i += 256) sH[i] = 0;
+
+    // ---- stage 0
+    for (int idx = tid; idx < RS * RS; idx += 256) {
+        const int cy = idx / RS, cx = idx - cy * RS;
+        const int x = clampi(x0 - HALO + cx, 0, w - 1), y = clampi(y0 - HALO + cy, 0, h - 1);
+        float2 f = make_float2(0.f, 0.f);
+        if (a.coarse) f = upsample_flow<false>(a.coarse + (size_t)j * a.coarse_stride, a.cw, a.ch, x, y, a.sxs, a.sys, a.fscale);
+        float m[5];
+        update_matrices_core<false>(x, y, f.x, f.y, w, h, R0, R1, a.plane, a.pitch, m);
+#pragma unroll
+        for (int c = 0; c < 5; c++) sM[c][cy][cx] = m[c];
+    }
+    __syncthreads();
+
+    const float k0 = a.win.k[0], k1 = a.win.k[1], ps = a.win.post_scale;
+#pragma unroll
+    for (int it = 0; it < NT; it++) {
+        const int hs = HALO - (it + 1);            // halo of this iteration's output region
+        const int side = T + 2 * hs, off = HALO - hs;
+        const bool last = it == NT - 1;
+        // (a) blur + solve: thread = (column, run of L rows); 3x3 window slides down in registers
+        const int runs = 256 / side, L = (side + runs - 1) / runs;
+        const int col = tid % side, run = tid / side;
+        const bool active = run < runs && run * L < side;
+        float win[3][3][5];                         // [row][col][channel]
+        const int r_begin = run * L, r_end = min(side, r_begin + L);
+        if (active) {
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+                for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+                    for (int c = 0; c < 5; c++) win[rr + 1][cc][c] = sM[c][off + r_begin - 1 + rr][off + col - 1 + cc];
+        }
+        for (int i = 0; i < L; i++) {
+            const int r = r_begin + i;
+            const bool ok = active && r < r_end;
+            float2 f = make_float2(0.f, 0.f);
+            if (ok) {
+#pragma unroll
+                for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+                    for (int c = 0; c < 5; c++) {
+                        win[0][cc][c] = win[1][cc][c]; win[1][cc][c] = win[2][cc][c];
+                        win[2][cc][c] = sM[c][off + r + 1][off + col - 1 + cc];
+                    }
+                float s[5];
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    float v0 = fmaf(win[0][0][c] + win[2][0][c], k1, win[1][0][c] * k0);
+                    float v1 = fmaf(win[0][1][c] + win[2][1][c], k1, win[1][1][c] * k0);
+                    float v2 = fmaf(win[0][2][c] + win[2][2][c], k1, win[1][2][c] * k0);
+                    s[c] = fmaf(v0 + v2, k1, v1 * k0) * ps;
+                }
+                f = solve_fast(s[0], s[1], s[2], s[3], s[4]);
+            }
+            if (last) {
+                const int x = x0 + col, y = y0 + r;
+                const bool in = ok && x < w && y < h;
+                if (in) reinterpret_cast<float2*>(a.out(j))[(size_t)y * w + x] = f;
+                if (do_hist) {
+                    const int key = in ? hist_key_fast(f.x, f.y) : -1;
+                    const unsigned peers = __match_any_sync(0xffffffffu, key);
+                    if (key >= 0 && (int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&sH[key], __popc(peers));
+                }
+            } else if (ok) {
+                sF[r * side + col] = f;
+            }
+        }
+        if (!last) {
+            __syncthreads();
+            // (b) M = updateMatrices(flow_i) on the same region; out-of-image cells take the clamped pixel
+            for (int idx = tid; idx < side * side; idx += 256) {
+                const int cy = idx / side, cx = idx - cy * side;
+                const int x = clampi(x0 - hs + cx, 0, w - 1), y = clampi(y0 - hs + cy, 0, h - 1);
+                const float2 f = sF[(y - (y0 - hs)) * side + (x - (x0 - hs))];
+                float m[5];
+                update_matrices_core<false>(x, y, f.x, f.y, w, h, R0, R1, a.plane, a.pitch, m);
+#pragma unroll
+                for (int c = 0; c < 5; c++) sM[c][off + cy][off + cx] = m[c];
+            }
+            __syncthreads();
+        }
+    }
+    if (do_hist) {
+        __syncthreads();
+        unsigned int* dst = a.hist_delta + (size_t)j * RC_HIST_CELLS;
+        for (int i = tid; i < RC_HIST_CELLS; i += 256)
+            if (sH[i]) atomicAdd(&dst[i], sH[i]);
+    }
 }
 
-template <bool FUSE_UPDATE>
-__global__ void update_flow_box_ref_kernel(Planes Min, int m, double scale, Planes R0, Planes R1, Planes Mout,
-                                           float* __restrict__ flow_out)
+// direction/speed key of one flow vector: bit-exact twin of aggregate.cu's hist_key (cv::cartToPolar restated,
+// SURVEY.md section 8(c)); intrinsics keep it independent of this file's FMA contraction.
+__device__ __forceinline__ int hist_key_fast(float x, float y)
 {
-    const int w = Min.w, h = Min.h;
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    double s[5] = {0, 0, 0, 0, 0};
-    for (int i = -m; i <= m; i++) {           // columns
-        int xx = clampi(x + i, 0, w - 1);
-        double v[5] = {0, 0, 0, 0, 0};
-        for (int j = -m; j <= m; j++) {       // vertical sum of that column
-            size_t o = (size_t)clampi(y + j, 0, h - 1) * Min.pitch + xx;
-#pragma unroll
-            for (int c = 0; c < 5; c++) v[c] += (double)__ldg(Min.plane(c) + o);
-        }
-#pragma unroll
-        for (int c = 0; c < 5; c++) s[c] += v[c];
-    }
-    float2 f = solve2x2(s[0] * scale, s[1] * scale, s[2] * scale, s[3] * scale, s[4] * scale);
-    if (FUSE_UPDATE) update_matrices_px(x, y, f.x, f.y, w, h, R0, R1, Mout);
-    else reinterpret_cast<float2*>(flow_out)[(size_t)y * w + x] = f;
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    float ax = fabsf(x), ay = fabsf(y);
+    float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float c = __fdiv_rn(mn, __fadd_rn(mx, 2.220446049250313e-16f));
+    float c2 = __fmul_rn(c, c);
+    float a = __fmul_rn(fmaf(fmaf(fmaf(p7, c2, p5), c2, p3), c2, p1), c);
+    if (ax < ay) a = __fsub_rn(90.f, a);
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    float mag = __fsqrt_rn(fmaf(x, x, __fmul_rn(y, y)));
+    int bin = (int)__fmul_rn(mag, (float)RC_HIST_RESOLUTION);
+    int dir = (int)__fdiv_rn(__fmul_rn(a, (float)RC_HIST_DIRECTIONS), 360.f);
+    if (bin < RC_HIST_BINS && bin >= 0) return dir * RC_HIST_BINS + bin;
+    return -1;
 }
 
-template <bool FUSE_UPDATE>
-__global__ void update_flow_gauss_ref_kernel(Planes Min, GaussWin gw, Planes R0, Planes R1, Planes Mout,
-                                             float* __restrict__ flow_out)
+// histogram of a batch of dense flows (used when the final iteration ran in the unfused path)
+__global__ void __launch_bounds__(256)
+hist_batch_kernel(FlowArgs a, int n)
 {
-    const int w = Min.w, h = Min.h, m = gw.m;
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    float hs[5];
-    auto vcol = [&](int xx, float* v) {
-        size_t o = (size_t)y * Min.pitch + xx;
-#pragma unroll
-        for (int c = 0; c < 5; c++) v[c] = __ldg(Min.plane(c) + o) * gw.k[0];
-        for (int j = 1; j <= m; j++) {
-            size_t ou = (size_t)clampi(y - j, 0, h - 1) * Min.pitch + xx;
-            size_t od = (size_t)clampi(y + j, 0, h - 1) * Min.pitch + xx;
-#pragma unroll
-            for (int c = 0; c < 5; c++) v[c] = v[c] + (__ldg(Min.plane(c) + od) + __ldg(Min.plane(c) + ou)) * gw.k[j];
-        }
-    };
-    float v0[5], va[5], vb[5];
-    vcol(x, v0);
-#pragma unroll
-    for (int c = 0; c < 5; c++) hs[c] = v0[c] * gw.k[0];
-    for (int i = 1; i <= m; i++) {
-        vcol(clampi(x - i, 0, w - 1), va);
-        vcol(clampi(x + i, 0, w - 1), vb);
-#pragma unroll
-        for (int c = 0; c < 5; c++) hs[c] = hs[c] + gw.k[i] * (va[c] + vb[c]);
+    __shared__ unsigned int sH[RC_HIST_CELLS];
+    const int j = blockIdx.y;
+    for (int i = threadIdx.x; i < RC_HIST_CELLS; i += 256) sH[i] = 0;
+    __syncthreads();
+    const float2* f = reinterpret_cast<const float2*>(a.out(j));
+    const int stride = gridDim.x * 256;
+    const int nround = (n + stride - 1) / stride * stride;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < nround; i += stride) {
+        int key = -1;
+        if (i < n) { float2 v = f[i]; key = hist_key_fast(v.x, v.y); }
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sH[key], __popc(peers));
     }
-    float2 f = solve2x2(hs[0], hs[1], hs[2], hs[3], hs[4]);
-    if (FUSE_UPDATE) update_matrices_px(x, y, f.x, f.y, w, h, R0, R1, Mout);
-    else reinterpret_cast<float2*>(flow_out)[(size_t)y * w + x] = f;
+    __syncthreads();
+    unsigned int* dst = a.hist_delta + (size_t)j * RC_HIST_CELLS;
+    for (int i = threadIdx.x; i < RC_HIST_CELLS; i += 256)
+        if (sH[i]) atomicAdd(&dst[i], sH[i]);
 }
 
 }  // namespace
@@ -310,63 +664,115 @@ __global__ void update_flow_gauss_ref_kernel(Planes Min, GaussWin gw, Planes R0,
 // ===================================================================================================
 // launchers
 // ===================================================================================================
-void rc_launch_pyr_layer(rc_ctx* c, const uint8_t* d_img, size_t step, int W, int H, Layer& L)
+static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
 {
-    const int two = !(L.w == W && L.h == H);
-    const double sx = 1.0 / ((double)L.w / (double)W), sy = 1.0 / ((double)L.h / (double)H);
-    dim3 b(32, 8);
-    dim3 g1((L.w + 31) / 32, (H + 7) / 8);
-    {
-        KScope ks(c, K_PYR_H, (double)W * H);
-        pyr_h_kernel<<<g1, b, 0, c->stream>>>(d_img, step, W, H, L.w, sx, two, L.smooth, L.htmp);
+    const int nslots = c->B + 1;
+    const size_t istride = (size_t)L.pitch * L.h;
+    KScope ks(c, K_POLYEXP, 24.0 * L.w * L.h * nb);
+    int np = c->strict ? 0 : (c->poly.n_eff + 3) / 4 * 4;
+    if (np > 16) np = 0;
+    if (np) {
+        PolyCoefF pf;
+        for (int i = 0; i <= RC_MAX_POLY_N; i++) { pf.g[i] = c->poly.g[i]; pf.xg[i] = c->poly.xg[i]; pf.xxg[i] = c->poly.xxg[i]; }
+        pf.ig11 = (float)c->poly.ig11; pf.ig03 = (float)c->poly.ig03; pf.ig33 = (float)c->poly.ig33; pf.ig55 = (float)c->poly.ig55;
+        const int TX = 128 - 2 * np;
+        dim3 g((L.w + TX - 1) / TX, (L.h + 31) / 32, nb);
+        switch (np) {
+        case 4: polyexp_fast_kernel<4><<<g, 256, 0, c->stream>>>(L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf); break;
+        case 8: polyexp_fast_kernel<8><<<g, 256, 0, c->stream>>>(L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf); break;
+        case 12: polyexp_fast_kernel<12><<<g, 256, 0, c->stream>>>(L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf); break;
+        default: polyexp_fast_kernel<16><<<g, 256, 0, c->stream>>>(L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf); break;
+        }
+        return;
     }
-    dim3 g2((L.w + 31) / 32, (L.h + 7) / 8);
-    const int pitch = (L.w + 31) / 32 * 32;
-    {
-        KScope ks(c, K_PYR_V, 4.0 * L.w * L.h);
-        pyr_v_kernel<<<g2, b, 0, c->stream>>>(L.htmp, W, H, L.w, L.h, sx, sy, two, L.smooth, L.I, pitch);
-    }
-}
-
-void rc_launch_polyexp(rc_ctx* c, const float* I, int w, int h, int pitch, const Planes& R)
-{
     constexpr int TX = 64, TY = 32;
     const int n = c->poly.n;
     const size_t smem = sizeof(float) * ((size_t)(TY + 2 * n) * (TX + 2 * n) + 3 * (size_t)TY * (TX + 2 * n));
     static size_t configured = 0;
     if (smem > configured) {
-        cudaFuncSetAttribute(polyexp_ref_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(polyexp_strict_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    dim3 g((w + TX - 1) / TX, (h + TY - 1) / TY);
-    KScope ks(c, K_POLYEXP, 24.0 * w * h);
-    polyexp_ref_kernel<TX, TY><<<g, 256, smem, c->stream>>>(I, w, h, pitch, R, c->poly);
+    dim3 g((L.w + TX - 1) / TX, (L.h + TY - 1) / TY, nb);
+    polyexp_strict_kernel<TX, TY><<<g, 256, smem, c->stream>>>(L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot,
+                                                              nslots, c->poly);
 }
 
-void rc_launch_update_matrices(rc_ctx* c, const Planes& R0, const Planes& R1, const Planes& M, int flow_mode,
-                               const float* flow, int cw, int ch, float flow_scale)
+void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, int nb, int first_slot)
 {
-    dim3 b(32, 8), g((R0.w + 31) / 32, (R0.h + 7) / 8);
-    double sx = 1.0, sy = 1.0;
-    if (flow_mode == 1) { sx = 1.0 / ((double)R0.w / (double)cw); sy = 1.0 / ((double)R0.h / (double)ch); }
-    KScope ks(c, K_UPDATE_MATRICES, (flow_mode ? 62.0 : 60.0) * R0.w * R0.h);
-    update_matrices_kernel<<<g, b, 0, c->stream>>>(R0, R1, M, flow_mode, flow, cw, ch, sx, sy, flow_scale);
+    const int W = c->prm.w, H = c->prm.h;
+    for (int k = 0; k < c->nlayers; k++) {
+        Layer& L = c->layer[k];
+        const int two = !(L.w == W && L.h == H);
+        const double sx = 1.0 / ((double)L.w / (double)W), sy = 1.0 / ((double)L.h / (double)H);
+        dim3 b(32, 8);
+        {
+            dim3 g1((L.w + 31) / 32, (H + 7) / 8, nb);
+            KScope ks(c, K_PYR_H, (double)W * H * nb);
+            pyr_h_kernel<<<g1, b, 0, c->stream>>>(d_frames, step, fstride, W, H, L.w, sx, two, L.smooth, L.htmp,
+                                                 L.htmp_stride);
+        }
+        {
+            dim3 g2((L.w + 31) / 32, (L.h + 7) / 8, nb);
+            KScope ks(c, K_PYR_V, 4.0 * L.w * L.h * nb);
+            pyr_v_kernel<<<g2, b, 0, c->stream>>>(L.htmp, L.htmp_stride, W, H, L.w, L.h, sx, sy, two, L.smooth, L.I,
+                                                 L.pitch, (size_t)L.pitch * L.h);
+        }
+        launch_polyexp(c, L, nb, first_slot);
+    }
 }
 
-void rc_launch_update_flow(rc_ctx* c, const Planes& M_in, const Planes& R0, const Planes& R1, const Planes& M_out,
-                           float* flow_out, unsigned long long* hist2d)
+void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_host, unsigned int* hist_delta)
 {
-    (void)hist2d;
-    dim3 b(32, 8), g((M_in.w + 31) / 32, (M_in.h + 7) / 8);
-    const bool fuse = M_out.p != nullptr;
-    KScope ks(c, fuse ? K_FLOW_ITER_FUSED : K_FLOW_ITER_FINAL, (fuse ? 80.0 : 28.0) * M_in.w * M_in.h);
-    if (c->prm.flags & RC_FARNEBACK_GAUSSIAN) {
-        if (fuse) update_flow_gauss_ref_kernel<true><<<g, b, 0, c->stream>>>(M_in, c->gwin, R0, R1, M_out, flow_out);
-        else update_flow_gauss_ref_kernel<false><<<g, b, 0, c->stream>>>(M_in, c->gwin, R0, R1, M_out, flow_out);
-    } else {
-        const int m = c->prm.winsize / 2;
-        const double scale = 1.0 / ((double)c->prm.winsize * c->prm.winsize);
-        if (fuse) update_flow_box_ref_kernel<true><<<g, b, 0, c->stream>>>(M_in, m, scale, R0, R1, M_out, flow_out);
-        else update_flow_box_ref_kernel<false><<<g, b, 0, c->stream>>>(M_in, m, scale, R0, R1, M_out, flow_out);
+    const int T = c->prm.iterations;
+    const bool fused_ok = !c->strict && c->win.m == 1 && T <= 3;
+    if (hist_delta) cudaMemsetAsync(hist_delta, 0, sizeof(unsigned int) * RC_HIST_CELLS * nb, c->stream);
+    for (int k = c->nlayers - 1; k >= 0; k--) {
+        Layer& L = c->layer[k];
+        FlowArgs a;
+        a.R = L.R; a.plane = L.plane; a.pitch = L.pitch; a.w = L.w; a.h = L.h; a.nslots = c->B + 1; a.prev_slot = prev_slot;
+        if (k == c->nlayers - 1) { a.coarse = nullptr; a.cw = a.ch = 0; a.coarse_stride = 0; a.sxs = a.sys = 1.0; a.fscale = 1.f; }
+        else {
+            Layer& C = c->layer[k + 1];
+            a.coarse = C.flow; a.cw = C.w; a.ch = C.h; a.coarse_stride = (size_t)C.w * C.h * 2;
+            a.sxs = 1.0 / ((double)L.w / (double)C.w); a.sys = 1.0 / ((double)L.h / (double)C.h);
+            a.fscale = (float)(1.0 / c->prm.pyr_scale);
+        }
+        a.M = L.M; a.m_stride = 2 * 5 * L.plane;
+        if (k == 0) { a.flow = nullptr; a.flow_stride = 0; for (int j = 0; j < nb; j++) a.flow_dst[j] = flow_dst_host[j]; }
+        else { a.flow = L.flow; a.flow_stride = (size_t)L.w * L.h * 2; }
+        a.hist_delta = (k == 0) ? hist_delta : nullptr;
+        a.win = c->win;
+        const double npx = (double)L.w * L.h * nb;
+        if (fused_ok) {
+            dim3 g((L.w + 31) / 32, (L.h + 31) / 32, nb);
+            KScope ks(c, K_FLOW_LAYER, (a.coarse ? 50.0 : 48.0) * npx);
+            if (T == 1) flow_layer_kernel<1><<<g, 256, 0, c->stream>>>(a);
+            else if (T == 2) flow_layer_kernel<2><<<g, 256, 0, c->stream>>>(a);
+            else flow_layer_kernel<3><<<g, 256, 0, c->stream>>>(a);
+            continue;
+        }
+        dim3 b(32, 8), g((L.w + 31) / 32, (L.h + 7) / 8, nb);
+        {
+            KScope ks(c, K_UPDATE_MATRICES, (a.coarse ? 62.0 : 60.0) * npx);
+            update_matrices_kernel<true><<<g, b, 0, c->stream>>>(a, 0);
+        }
+        int mi = 0;
+        for (int it = 0; it < T; it++) {
+            if (it < T - 1) {
+                KScope ks(c, K_FLOW_ITER_FUSED, 80.0 * npx);
+                update_flow_strict_kernel<true><<<g, b, 0, c->stream>>>(a, mi);
+                mi ^= 1;
+            } else {
+                KScope ks(c, K_FLOW_ITER_FINAL, 28.0 * npx);
+                update_flow_strict_kernel<false><<<g, b, 0, c->stream>>>(a, mi);
+            }
+        }
+        if (k == 0 && hist_delta) {
+            const int n = L.w * L.h;
+            int gx = (n + 255) / 256; if (gx > 148 * 4) gx = 148 * 4;
+            KScope ks(c, K_POLAR_HIST, 8.0 * npx);
+            hist_batch_kernel<<<dim3(gx, nb), 256, 0, c->stream>>>(a, n);
+        }
     }
 }

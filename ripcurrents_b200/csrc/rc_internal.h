@@ -12,20 +12,21 @@
 #define RC_MAX_POLY_N 32
 #define RC_MAX_SMOOTH_TAPS 255
 #define RC_MAX_WIN_HALF 64
+#define RC_MAX_BATCH 64
+#define RC_THR_FLOATS 80       // per-frame thresholds record: [0] UPPER, [1..36] UPPER2d, [37..72] prop, [74..75] int64 histsum
+#define RC_HIST_CELLS (RC_HIST_ROWS * RC_HIST_BINS)
 
-// Planar fp32 image set: `planes` planes of h rows, row pitch `pitch` floats, plane stride `pstride` floats.
-struct Planes {
-    float* p = nullptr;
-    int w = 0, h = 0, pitch = 0;
-    size_t pstride = 0;
-    __host__ __device__ float* plane(int c) const { return p + (size_t)c * pstride; }
-};
+// kernel classes for rc_profile_* (per-launch CUDA-event timing) -- order matches rc_kernel_names[]
+enum RcKernelId { K_PYR_H = 0, K_PYR_V, K_POLYEXP, K_UPDATE_MATRICES, K_FLOW_ITER_FUSED, K_FLOW_ITER_FINAL,
+                  K_FLOW_LAYER, K_POLAR_HIST, K_THRESHOLDS, K_CLASSIFY, K_WINDOW, K_ADVECT, K_STREAKLINE, K_MISC,
+                  K_COUNT };
+extern const char* const rc_kernel_names[K_COUNT];
 
-struct PolyCoef {          // polynomial-expansion kernels
+struct PolyCoef {          // polynomial-expansion kernels; entries beyond n are zero
     float g[RC_MAX_POLY_N + 1], xg[RC_MAX_POLY_N + 1], xxg[RC_MAX_POLY_N + 1];
     double ig11, ig03, ig33, ig55;
     int n;        // poly_n
-    int n_eff;    // taps actually evaluated (== n in strict mode)
+    int n_eff;    // taps evaluated by the fast kernel (== n in strict mode)
 };
 
 struct SmoothCoef {        // presmooth kernel of one pyramid layer (A.2)
@@ -33,9 +34,12 @@ struct SmoothCoef {        // presmooth kernel of one pyramid layer (A.2)
     int ksize;
 };
 
-struct GaussWin {          // updateFlow Gaussian window (A.7)
+struct WinCoef {           // updateFlow window: box (all ones, post-scale 1/winsize^2) or Gaussian (A.7, post-scale 1)
     float k[RC_MAX_WIN_HALF + 1];
     int m;
+    float post_scale;      // fp32 post scale used by the fast kernels
+    double post_scale_d;   // fp64 post scale used by the strict kernels
+    int gaussian;
 };
 
 struct FarnebackParams {
@@ -44,41 +48,48 @@ struct FarnebackParams {
     int levels = 0, winsize = 0, iterations = 0, poly_n = 0;
     double poly_sigma = 0;
     int flags = 0;
+    int max_batch = 1;
     bool operator==(const FarnebackParams& o) const {
         return w == o.w && h == o.h && pyr_scale == o.pyr_scale && levels == o.levels && winsize == o.winsize &&
-               iterations == o.iterations && poly_n == o.poly_n && poly_sigma == o.poly_sigma && flags == o.flags;
+               iterations == o.iterations && poly_n == o.poly_n && poly_sigma == o.poly_sigma && flags == o.flags &&
+               max_batch == o.max_batch;
     }
 };
 
+// One pyramid layer.  All arrays carry a leading batch / ring dimension.
+//   I     [B]      presmoothed layer image of each new frame of the batch (row pitch `pitch`)
+//   htmp  [B]      pass-1 scratch of the pyramid kernel (H rows x 2*w floats)
+//   R     [B+1]    ring of polynomial expansions, 5 planes each (plane = pitch*h floats)
+//   M     [B][2]   G/h matrices ping-pong, 5 planes each (only the unfused path uses them)
+//   flow  [B]      dense w*h*2 (layers k >= 1; layer 0 writes into the context's flow ring)
 struct Layer {
-    int w = 0, h = 0;
+    int w = 0, h = 0, pitch = 0;
+    size_t plane = 0;
     SmoothCoef smooth;
-    float* I = nullptr;            // w*h (pitch) fp32 presmoothed layer image of the frame being expanded
-    float* htmp = nullptr;         // pass-1 scratch of the pyramid kernel
-    Planes R[2];                   // polynomial expansion of the two cached frames (ping-pong)
-    Planes M[2];                   // G/h matrices (ping-pong across iterations)
-    float* flow = nullptr;         // w*h*2 fp32 (dense) flow of this layer
+    float* I = nullptr;
+    float* htmp = nullptr;
+    float* R = nullptr;
+    float* M = nullptr;
+    float* flow = nullptr;
+    size_t htmp_stride = 0;      // floats per batch element
+    __host__ __device__ float* Rslot(int s) const { return R + (size_t)s * 5 * plane; }
 };
-
-// kernel classes for rc_profile_* (per-launch CUDA-event timing) -- order matches rc_kernel_names[]
-enum RcKernelId { K_PYR_H = 0, K_PYR_V, K_POLYEXP, K_UPDATE_MATRICES, K_FLOW_ITER_FUSED, K_FLOW_ITER_FINAL,
-                  K_POLAR_HIST, K_THRESHOLDS, K_CLASSIFY, K_WINDOW, K_ADVECT, K_STREAKLINE, K_MISC, K_COUNT };
-extern const char* const rc_kernel_names[K_COUNT];
 
 struct ProfRec { int id; cudaEvent_t a, b; double bytes; };
 
 struct rc_ctx {
     int device = 0;
-    bool prof_on = false;
-    std::vector<ProfRec> prof;          // pending records (events not yet read)
-    std::vector<cudaEvent_t> ev_pool;   // recycled events
-    double prof_ms[K_COUNT] = {0};
-    double prof_bytes[K_COUNT] = {0};
-    int64_t prof_n[K_COUNT] = {0};
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
     int64_t launches = 0;
+
+    bool prof_on = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms[K_COUNT] = {0};
+    double prof_bytes[K_COUNT] = {0};
+    int64_t prof_n[K_COUNT] = {0};
 
     // Farneback state
     bool configured = false;
@@ -86,37 +97,52 @@ struct rc_ctx {
     int nlayers = 0;
     Layer layer[RC_MAX_LAYERS];
     PolyCoef poly;
-    GaussWin gwin;
-    uint8_t* d_frame = nullptr;    // staging for a host frame (w*h u8, dense)
-    size_t d_frame_cap = 0;
-    int cur = 0;                   // R[cur] holds the most recent frame
-    int frames_seen = 0;
-    bool have_flow = false;
-    float* flow_out = nullptr;     // == layer[0].flow
+    WinCoef win;
+    bool strict = false;
+    int B = 1;                     // max batch
+    int r_base = 0;                // ring slot (in R) of the most recent expanded frame
+    long long frames_seen = 0;
+    int n_flows = 0;               // flows produced by the last push (0..B)
     std::vector<void*> allocs;
 
-    // pinned staging
-    void* h_pin = nullptr;
-    size_t h_pin_cap = 0;
-    void* d_tmp = nullptr;         // generic device scratch for host-pointer arguments
-    size_t d_tmp_cap = 0;
-    void* d_tmp2 = nullptr;
-    size_t d_tmp2_cap = 0;
+    // flow ring: layer-0 flows of the most recent frames; slot of frame-pair index p is p % ring_slots
+    float* flow_ring = nullptr;
+    int ring_slots = 0;
+    long long pairs_done = 0;      // total flows produced since configure
+    int win_W = 0;                 // sliding-window length (0 = off)
+    float* d_avg = nullptr;        // window mean (w*h*2)
+
+    // staging for host frames (double-buffered) and outputs
+    uint8_t* d_frames[2] = {nullptr, nullptr};
+    uint8_t* d_masks[2] = {nullptr, nullptr};
+    float* d_thr_batch[2] = {nullptr, nullptr};    // [B][RC_THR_FLOATS] per staging slot
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr};     // H2D of slot finished
+    cudaEvent_t ev_compute[2] = {nullptr, nullptr};// kernels that read/wrote slot finished
+    cudaEvent_t ev_out[2] = {nullptr, nullptr};    // D2H of slot finished
+    long long submitted = 0;                       // batches submitted through the async path
+    int slot_frames[2] = {0, 0};                   // frames staged in each slot (for rc_wait)
+    float* h_thr[2] = {nullptr, nullptr};          // pinned host mirror of d_thr_batch
+    rc_frame_result* pending_results[2] = {nullptr, nullptr};
+    int pending_count[2] = {0, 0};
+    int pending_first_produced[2] = {0, 0};
+
+    // generic scratch for host-pointer arguments
+    void* d_tmp = nullptr;  size_t d_tmp_cap = 0;
+    void* d_tmp2 = nullptr; size_t d_tmp2_cap = 0;
 
     // aggregation state
-    unsigned long long* d_hist2d = nullptr;   // RC_HIST_ROWS*RC_HIST_BINS
-    float* d_thr = nullptr;                   // [0]=UPPER, [1..36]=UPPER2d, [37..72]=prop, then int64 histsum
-    float* d_acc = nullptr;                   // accumulator.x, acc_w*acc_h
+    unsigned long long* d_hist2d = nullptr;   // cumulative counters, RC_HIST_CELLS
+    unsigned int* d_hist_delta = nullptr;     // [B][RC_HIST_CELLS] per-frame counts of the current batch
+    float* d_thr = nullptr;                   // thresholds of the most recent frame (RC_THR_FLOATS)
+    float* d_acc = nullptr;                   // accumulator.x
     int acc_w = 0, acc_h = 0;
-    uint8_t* d_mask = nullptr;                // outmask scratch
-    uint8_t* d_cls = nullptr;                 // waveclass / waterclass scratch (2 planes)
+    uint8_t* d_cls = nullptr;                 // waveclass / waterclass scratch (2 planes) for rc_classify_accumulate
 
-    // sliding window
-    int win_W = 0, win_w = 0, win_h = 0, win_i = 0;
-    float* d_ring = nullptr;                  // W slots of w*h*2
-    float* d_avg = nullptr;
-
-    // advection scratch handled through d_tmp
+    // stand-alone window (rc_window_* with caller-provided flows)
+    int swin_W = 0, swin_w = 0, swin_h = 0, swin_i = 0;
+    float* d_swin_ring = nullptr;
+    float* d_swin_avg = nullptr;
 };
 
 // RAII bracket around one kernel launch: counts it and, when profiling is on, times it with two CUDA events on
@@ -141,24 +167,29 @@ struct KScope {
     }
 };
 
-// ---- kernel launchers (farneback.cu) -------------------------------------------------------------
-void rc_launch_pyr_layer(rc_ctx* c, const uint8_t* d_img, size_t step, int W, int H, Layer& L);
-void rc_launch_polyexp(rc_ctx* c, const float* I, int w, int h, int pitch, const Planes& R);
-// flow_mode: 0 zero flow, 1 upsample `coarse` (cw x ch) and scale, 2 read `flow` (w x h)
-void rc_launch_update_matrices(rc_ctx* c, const Planes& R0, const Planes& R1, const Planes& M, int flow_mode,
-                               const float* flow, int cw, int ch, float flow_scale);
-// one updateFlow iteration: blur M_in, solve; if M_out.p: fused updateMatrices into M_out, else write flow_out.
-// hist2d != nullptr additionally bins the produced flow (A2+A3 fused into the final iteration of layer 0).
-void rc_launch_update_flow(rc_ctx* c, const Planes& M_in, const Planes& R0, const Planes& R1, const Planes& M_out,
-                           float* flow_out, unsigned long long* hist2d);
+// ---- farneback.cu ----------------------------------------------------------------------------------
+// Expands `nb` new frames (device, dense u8, frame stride `fstride`) into R ring slots first_slot.. (mod B+1).
+void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, int nb, int first_slot);
+// Flows for `nb` consecutive pairs: pair j = (ring slot (prev_slot + j) % (B+1), next slot); layer-0 flow of pair j
+// goes to flow_dst[j]; hist_delta (may be null) receives per-pair direction/speed counts [nb][RC_HIST_CELLS].
+void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_host, unsigned int* hist_delta);
 
 // ---- aggregate.cu ----------------------------------------------------------------------------------
 void rc_launch_polar_hist(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, unsigned long long* hist2d);
 void rc_launch_cart_to_polar(rc_ctx* c, const float* flow, size_t n, float* mag, float* ang);
-void rc_launch_thresholds(rc_ctx* c, const unsigned long long* hist2d, float* thr);
+// cumulative += delta[j] for j < nb, thresholds after each frame -> thr_batch[j]; last also copied to thr_last
+void rc_launch_thresholds_batch(rc_ctx* c, unsigned long long* hist2d, const unsigned int* delta, int nb,
+                                float* thr_batch, float* thr_last);
 void rc_launch_classify(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float upper, const float* thr,
-                        int framecount, float* acc, uint8_t* mask, uint8_t* waveclass, uint8_t* waterclass,
-                        float* ring_old, float* avg, int W);
+                        int framecount, float* acc, uint8_t* mask, uint8_t* waveclass, uint8_t* waterclass);
+// batched classify + accumulate + mask (+ sliding-window mean) over nb consecutive flows held in the flow ring
+struct ClassifyBatch {
+    const float* flow[RC_MAX_BATCH];      // flow of frame j
+    const float* old[RC_MAX_BATCH];       // ring slot leaving the window at frame j (null while the window fills)
+    int nb;
+};
+void rc_launch_classify_batch(rc_ctx* c, const ClassifyBatch& cb, int w, int h, const float* thr_batch, int framecount0,
+                              float* acc, uint8_t* masks, float* avg, int W);
 void rc_launch_window_update(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float* slot, float* avg,
                              int W);
 void rc_launch_subtract_mean(rc_ctx* c, float* flow, size_t flow_step, int w, int h, double* d_sums);
@@ -168,6 +199,3 @@ void rc_launch_advect(rc_ctx* c, const float* flow, size_t flow_step, int w, int
                       int iterations, float upper, int variant, float* dist, const int32_t* home);
 void rc_launch_streakline(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, const float* emitters, int E,
                           float* vertices, int32_t* count, int cap, float dt);
-
-// thresholds buffer layout (floats): [0] UPPER, [1..36] UPPER2d, [37..72] prop_above_upper
-#define RC_THR_FLOATS 80

@@ -150,3 +150,72 @@ def test_process_frame_matches_separate_calls(ctx, oracle):
         assert np.array_equal(ctx.window_get().ravel(), avg)
     assert np.array_equal(ctx.accumulator_get(w, h).ravel(), acc)
     other.close()
+
+
+def test_process_frames_batched(ctx, oracle):
+    """rc_process_frames over batches == the frame-by-frame reference order: per-frame cumulative histograms and
+    thresholds, accumulator gate at framecount > 30, masks, and the W-frame window mean (W < batch and W > batch)."""
+    from ripcurrents_b200 import Context, synth
+    w, h = 256, 160
+    fr = np.stack(synth.clip(w, h, 14, seed=31))
+    P = (0.5, 2, 3, 2, 15, 1.2, 0)
+    other = Context(0)
+    flows = [other.farneback(fr[i], fr[i + 1], *P).copy() for i in range(13)]
+    other.close()
+    for W, B in [(3, 5), (6, 4)]:
+        c = Context(0)
+        c.flow_configure_batch(w, h, *P, B)
+        c.hist_reset(); c.window_configure(w, h, W)
+        st = oracle.HistState(); acc = np.zeros(h * w, np.float32)
+        avg = np.zeros(h * w * 2, np.float32); ring = np.zeros((W, h * w * 2), np.float32)
+        masks = np.zeros((B, h, w), np.uint8)
+        fc0, pair = 25, 0
+        for lo in range(0, 14, B):
+            hi = min(14, lo + B)
+            n, res = c.process_frames(np.ascontiguousarray(fr[lo:hi]), fc0 + lo, masks)
+            first = 1 if lo == 0 else 0
+            assert n == hi - lo - first
+            for i in range(hi - lo):
+                if i < first:
+                    assert res[i].produced == 0
+                    continue
+                fc = fc0 + lo + i
+                flow = flows[pair]
+                oracle.histogram(flow, st)
+                up, up2, prop = oracle.thresholds(st)
+                assert res[i].produced == 1 and res[i].UPPER == up and res[i].histsum == int(st.histsum[0])
+                assert np.array_equal(np.array(res[i].UPPER2d[:], np.float32), up2)
+                rmask, _, _ = oracle.classify_accumulate(flow, up, fc, acc)
+                assert np.array_equal(masks[i], rmask), (W, B, lo, i)
+                oracle.window_update(avg, ring[pair % W], flow, W)
+                pair += 1
+            assert np.array_equal(c.window_get().ravel(), avg), (W, B, lo)
+        assert np.array_equal(c.accumulator_get(w, h).ravel(), acc)
+        assert np.array_equal(c.hist_get()[2], st.hist2d)
+        c.close()
+
+
+def test_submit_async_matches_sync(ctx):
+    """rc_submit_frames / rc_wait (double-buffered copies on side streams) gives the same masks and thresholds."""
+    import ctypes as C
+    from ripcurrents_b200 import Context, capi, synth
+    w, h, B = 192, 128, 3
+    fr = np.stack(synth.clip(w, h, 13, seed=41))
+    P = (0.5, 2, 3, 2, 15, 1.2, 0)
+    ref = Context(0); ref.flow_configure_batch(w, h, *P, B); ref.hist_reset()
+    rmasks = np.zeros((13, h, w), np.uint8); rres = []
+    for lo in range(0, 12, B):
+        n, res = ref.process_frames(np.ascontiguousarray(fr[lo:lo + B]), 40 + lo, rmasks[lo:lo + B])
+        rres += [(r.produced, r.UPPER, r.histsum) for r in res]
+    ref.close()
+    c = Context(0); c.flow_configure_batch(w, h, *P, B); c.hist_reset()
+    masks = np.zeros((13, h, w), np.uint8)
+    results = [(capi.FrameResult * B)() for _ in range(4)]
+    for k, lo in enumerate(range(0, 12, B)):
+        c.process_frames(np.ascontiguousarray(fr[lo:lo + B]), 40 + lo, masks[lo:lo + B], submit_only=True,
+                         results=results[k])
+    c.wait()
+    got = [(r.produced, r.UPPER, r.histsum) for rs in results for r in rs]
+    assert got == rres
+    assert np.array_equal(masks[1:12], rmasks[1:12])
+    c.close()

@@ -152,3 +152,37 @@ def test_translation_recovered(ctx):
     flow = ctx.farneback(fr[0], fr[1], 0.5, 2, 10, 3, 15, 1.2, 256)
     inner = flow[100:-100, 100:-100]
     assert abs(float(np.median(inner[..., 0])) - 1.0) < 0.05 and abs(float(np.median(inner[..., 1])) - 0.5) < 0.05
+
+
+@pytest.mark.parametrize("mode", [0, STRICT])
+def test_batched_equals_streaming(ctx, mode):
+    """rc_flow_push_batch (all kernels over a batch, ring of cached expansions) == frame-by-frame, bit for bit,
+    across batch boundaries, a partial batch, and a priming frame inside the first batch."""
+    from ripcurrents_b200 import Context, synth
+    w, h = 300, 200
+    fr = np.stack(synth.clip(w, h, 12, seed=21))
+    P = (0.5, 2, 3, 2, 15, 1.2, mode)
+    single = [ctx.farneback(fr[i], fr[i + 1], *P).copy() for i in range(11)]
+    c2 = Context(0)
+    c2.flow_configure_batch(w, h, *P, 4)
+    flows = np.empty((4, h, w, 2), np.float32)
+    got = []
+    for lo, hi in [(0, 4), (4, 8), (8, 10), (10, 12)]:
+        n = c2.flow_push_batch(np.ascontiguousarray(fr[lo:hi]), flows=flows)
+        got += [flows[j].copy() for j in range(n)]
+    assert len(got) == 11
+    for i in range(11):
+        assert np.array_equal(got[i], single[i]), i
+    assert np.array_equal(c2.flow_host_at(0), single[10]) and np.array_equal(c2.flow_host_at(1), single[9])
+    c2.close()
+
+
+def test_fast_vs_strict_close(ctx):
+    """The default (fp32 / truncated-tail) arithmetic stays within 1e-3 px of the strict fp64 one everywhere."""
+    from ripcurrents_b200 import synth
+    fr = synth.clip(640, 480, 2, seed=8)
+    for P in [(0.5, 2, 3, 2, 15, 1.2, 0), (0.5, 2, 3, 3, 7, 1.5, 0), (0.5, 2, 2, 1, 5, 1.1, 0)]:
+        a = ctx.farneback(fr[0], fr[1], *P).copy()
+        b = ctx.farneback(fr[0], fr[1], *(P[:6] + (STRICT,)))
+        mean, mx = epe(a, b)
+        assert mean <= 1e-5 and mx <= 1e-3, (P, mean, mx)
