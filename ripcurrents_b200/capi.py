@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "lib", "libripcurrents_b200.so")
+SO_PATH = os.environ.get("RC_B200_LIB") or os.path.join(_HERE, "lib", "libripcurrents_b200.so")   # env: A/B builds
 
 HIST_BINS, HIST_DIRECTIONS, HIST_RESOLUTION, HIST_ROWS = 50, 36, 20, 37
 FARNEBACK_GAUSSIAN = 256

@@ -79,63 +79,65 @@ __global__ void cart_to_polar_kernel(const float* __restrict__ flow, size_t n, f
     mag[i] = m; ang[i] = a;
 }
 
-// Thresholds (ripcurrents.cpp:333-366) after each frame of a batch: cumulative += delta[j], then the tail scans.
-// One CTA; thread a < 36 owns direction a; thread 0 also does the global threshold.
+// Thresholds (ripcurrents.cpp:333-366) after each frame of a batch.  CTA j owns frame j: it forms the cumulative
+// counts through its frame (base + delta[0..j]) and runs the tail scans; thread a < 36 owns direction a, thread 0
+// also does the global threshold.  The last CTA's sums become the new cumulative counters (histnext), so the batch
+// is one parallel launch instead of nb dependent ones.
 __global__ void __launch_bounds__(256)
-thresholds_batch_kernel(unsigned long long* __restrict__ hist2d, const unsigned int* __restrict__ delta, int nb,
-                        float* __restrict__ thr_batch, float* __restrict__ thr_last)
+thresholds_batch_kernel(const unsigned long long* __restrict__ hist2d, unsigned long long* __restrict__ histnext,
+                        const unsigned int* __restrict__ delta, int nb, float* __restrict__ thr_batch,
+                        float* __restrict__ thr_last)
 {
     __shared__ long long cum[RC_HIST_CELLS];
     __shared__ long long hist[RC_HIST_BINS];
     __shared__ long long s_threshsum;
     __shared__ int s_target;
-    const int t = threadIdx.x;
-    for (int i = t; i < RC_HIST_CELLS; i += blockDim.x) cum[i] = (long long)hist2d[i];
-    __syncthreads();
-    const int nframes = nb > 0 ? nb : 1;
-    for (int j = 0; j < nframes; j++) {
-        if (nb > 0) {
-            for (int i = t; i < RC_HIST_CELLS; i += blockDim.x) cum[i] += (long long)delta[(size_t)j * RC_HIST_CELLS + i];
-            __syncthreads();
-        }
-        float* thr = thr_batch ? thr_batch + (size_t)j * RC_THR_FLOATS : thr_last;
-        if (t < RC_HIST_BINS) {
-            long long s = 0;
-            for (int a = 0; a < RC_HIST_ROWS; a++) s += cum[a * RC_HIST_BINS + t];
-            hist[t] = s;
-        }
-        __syncthreads();
-        if (t == 0) {
-            long long histsum = 0;
-            for (int b = 0; b < RC_HIST_BINS; b++) histsum += hist[b];
-            long long threshsum = 0;
-            int bin = RC_HIST_BINS - 1;
-            while ((double)threshsum < ((double)histsum * .05)) { threshsum += hist[bin]; bin--; }
-            thr[0] = __fdiv_rn((float)bin, (float)RC_HIST_RESOLUTION);
-            s_threshsum = threshsum; s_target = bin;
-            reinterpret_cast<long long*>(thr + 74)[0] = histsum;   // 8-byte aligned slot after the 73 floats
-        }
-        __syncthreads();
-        if (t < RC_HIST_DIRECTIONS) {
-            const long long* row = cum + t * RC_HIST_BINS;
-            long long sum = 0;
-            for (int b = 0; b < RC_HIST_BINS; b++) sum += row[b];
-            long long t2 = 0, t3 = 0;
-            int b = RC_HIST_BINS - 1;
-            while ((double)t2 < ((double)sum * .05)) { t2 += row[b]; b--; }
-            float u = __fdiv_rn((float)b, (float)RC_HIST_RESOLUTION);
-            if ((double)u < 0.01) u = (float)0.01;
-            thr[1 + t] = u;
-            b = RC_HIST_BINS - 1;
-            while (b > s_target) { t3 += row[b]; b--; }
-            thr[37 + t] = __fdiv_rn((float)t3, (float)s_threshsum);
-        }
-        __syncthreads();
-        if (thr_batch && thr_last && j == nframes - 1)
-            for (int i = t; i < RC_THR_FLOATS; i += blockDim.x) thr_last[i] = thr[i];
+    const int t = threadIdx.x, j = blockIdx.x;
+    const int nd = nb > 0 ? j + 1 : 0;
+    for (int i = t; i < RC_HIST_CELLS; i += blockDim.x) {
+        long long s = (long long)hist2d[i];
+        for (int d = 0; d < nd; d++) s += (long long)delta[(size_t)d * RC_HIST_CELLS + i];
+        cum[i] = s;
     }
-    if (nb > 0)
-        for (int i = t; i < RC_HIST_CELLS; i += blockDim.x) hist2d[i] = (unsigned long long)cum[i];
+    __syncthreads();
+    const bool is_last = nb <= 0 || j == nb - 1;
+    float* thr = thr_batch ? thr_batch + (size_t)j * RC_THR_FLOATS : thr_last;
+    if (t < RC_HIST_BINS) {
+        long long s = 0;
+        for (int a = 0; a < RC_HIST_ROWS; a++) s += cum[a * RC_HIST_BINS + t];
+        hist[t] = s;
+    }
+    __syncthreads();
+    if (t == 0) {
+        long long histsum = 0;
+        for (int b = 0; b < RC_HIST_BINS; b++) histsum += hist[b];
+        long long threshsum = 0;
+        int bin = RC_HIST_BINS - 1;
+        while ((double)threshsum < ((double)histsum * .05)) { threshsum += hist[bin]; bin--; }
+        thr[0] = __fdiv_rn((float)bin, (float)RC_HIST_RESOLUTION);
+        s_threshsum = threshsum; s_target = bin;
+        reinterpret_cast<long long*>(thr + 74)[0] = histsum;   // 8-byte aligned slot after the 73 floats
+    }
+    __syncthreads();
+    if (t < RC_HIST_DIRECTIONS) {
+        const long long* row = cum + t * RC_HIST_BINS;
+        long long sum = 0;
+        for (int b = 0; b < RC_HIST_BINS; b++) sum += row[b];
+        long long t2 = 0, t3 = 0;
+        int b = RC_HIST_BINS - 1;
+        while ((double)t2 < ((double)sum * .05)) { t2 += row[b]; b--; }
+        float u = __fdiv_rn((float)b, (float)RC_HIST_RESOLUTION);
+        if ((double)u < 0.01) u = (float)0.01;
+        thr[1 + t] = u;
+        b = RC_HIST_BINS - 1;
+        while (b > s_target) { t3 += row[b]; b--; }
+        thr[37 + t] = __fdiv_rn((float)t3, (float)s_threshsum);
+    }
+    __syncthreads();
+    if (is_last) {
+        if (thr_batch && thr_last) for (int i = t; i < RC_THR_FLOATS; i += blockDim.x) thr_last[i] = thr[i];
+        if (nb > 0) for (int i = t; i < RC_HIST_CELLS; i += blockDim.x) histnext[i] = (unsigned long long)cum[i];
+    }
 }
 
 // classify (mag > UPPER -> accumulator2.x = 1), accumulate when framecount > 30, mask/out classes: single frame
@@ -323,7 +325,10 @@ void rc_launch_thresholds_batch(rc_ctx* c, unsigned long long* hist2d, const uns
                                 float* thr_batch, float* thr_last)
 {
     KScope ks(c, K_THRESHOLDS, (8.0 + 4.0 * nb) * RC_HIST_CELLS);
-    thresholds_batch_kernel<<<1, 256, 0, c->stream>>>(hist2d, delta, nb, thr_batch, thr_last);
+    // CTAs read the old counters and the last one writes the new ones: double-buffered to keep the launch race-free
+    unsigned long long* next = nb > 0 ? hist2d + RC_HIST_CELLS : hist2d;
+    thresholds_batch_kernel<<<nb > 0 ? nb : 1, 256, 0, c->stream>>>(hist2d, next, delta, nb, thr_batch, thr_last);
+    if (nb > 0) cudaMemcpyAsync(hist2d, next, sizeof(unsigned long long) * RC_HIST_CELLS, cudaMemcpyDeviceToDevice, c->stream);
 }
 
 void rc_launch_classify(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float upper, const float* thr,

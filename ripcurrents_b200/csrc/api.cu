@@ -9,7 +9,7 @@
 
 #define RC_VERSION 101
 
-const char* const rc_kernel_names[K_COUNT] = {"pyr_h", "pyr_v", "polyexp", "update_matrices", "flow_iter_fused",
+const char* const rc_kernel_names[K_COUNT] = {"pyr_unused", "pyramid", "polyexp", "update_matrices", "flow_iter_fused",
                                               "flow_iter_final", "flow_layer_fused", "polar_hist", "thresholds",
                                               "classify", "window_mean", "advect", "streakline", "misc"};
 
@@ -162,8 +162,9 @@ void make_win(WinCoef& g, int winsize, bool gaussian)
 int ensure_aggregate(rc_ctx* c)
 {
     if (c->d_hist2d) return RC_OK;
-    CUDA_TRY(c, cudaMalloc((void**)&c->d_hist2d, sizeof(unsigned long long) * RC_HIST_CELLS));
-    CUDA_TRY(c, cudaMemsetAsync(c->d_hist2d, 0, sizeof(unsigned long long) * RC_HIST_CELLS, c->stream));
+    // [0, CELLS): the cumulative counters; [CELLS, 2*CELLS): scratch for the batched thresholds launch
+    CUDA_TRY(c, cudaMalloc((void**)&c->d_hist2d, sizeof(unsigned long long) * RC_HIST_CELLS * 2));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_hist2d, 0, sizeof(unsigned long long) * RC_HIST_CELLS * 2, c->stream));
     CUDA_TRY(c, cudaMalloc((void**)&c->d_thr, sizeof(float) * RC_THR_FLOATS));
     CUDA_TRY(c, cudaMemsetAsync(c->d_thr, 0, sizeof(float) * RC_THR_FLOATS, c->stream));
     return RC_OK;
@@ -480,7 +481,6 @@ int rc_flow_configure_batch(rc_ctx* c, int w, int h, double pyr_scale, int level
         L.htmp_stride = 2 * (size_t)L.w * h;
         const bool fused = !c->strict && winsize / 2 == 1 && iterations <= 3;
         if ((rc = dev_alloc(c, (void**)&L.I, sizeof(float) * L.plane * B)) ||
-            (rc = dev_alloc(c, (void**)&L.htmp, sizeof(float) * L.htmp_stride * B)) ||
             (rc = dev_alloc(c, (void**)&L.R, sizeof(float) * 5 * L.plane * (B + 1))) ||
             (!fused && (rc = dev_alloc(c, (void**)&L.M, sizeof(float) * 2 * 5 * L.plane * B))) ||
             (k > 0 && (rc = dev_alloc(c, (void**)&L.flow, sizeof(float) * 2 * (size_t)L.w * L.h * B))))

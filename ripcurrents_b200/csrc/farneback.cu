@@ -9,9 +9,11 @@
 //   fast   : (default) fp32 with FMA, Gaussian tails of the expansion kernel below 1e-9 of the centre dropped,
 //            2x2 solve in fp32 with error-free determinants.  Measured as close to cv2 as the strict mode is.
 //
-// HBM layout: per-pixel coefficient sets are PLANAR fp32 (5 planes for the polynomial expansion R and for the
-// structure matrices M), row pitch rounded up to 32 floats, so a warp reads 128 contiguous bytes from each plane;
-// flow is interleaved float2 (CV_32FC2, the output format).  Every array has a leading batch dimension: one
+// HBM layout: the polynomial expansion R of a frame is stored "4+1": one float4 plane {dI/dy, dI/dx, Iyy, Ixx} and
+// one float plane {Ixy} (row pitch rounded up to 32 pixels), so that the data-dependent bilinear gather of
+// updateMatrices costs 4 x (16 B + 4 B) loads instead of 20 scalar ones and every access of a warp is a run of
+// full 32-byte sectors; the structure matrices M of the unfused path are 5 fp32 planes; flow is interleaved float2
+// (CV_32FC2, the output format).  Every array has a leading batch dimension: one
 // launch processes all frame pairs of a batch (blockIdx.z), which is what fills 148 SMs on the small pyramid layers.
 #include "rc_internal.h"
 
@@ -41,72 +43,140 @@ __device__ __forceinline__ void resize_coef(int d, int src, double scale, int& s
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Pyramid layer k of one frame: u8 -> fp32, Gaussian blur of the FULL-RESOLUTION image (REFLECT_101,
-// rows then columns, fp32), bilinear resize to (lw, lh).  The blur is evaluated only where the resize samples.
-// pass 1: horizontal blur at the (up to) two source columns each destination column samples, every source row.
+// Pyramid layer k of one frame (Appendix A.2): u8 -> fp32, Gaussian blur of the FULL-RESOLUTION image
+// (REFLECT_101, rows then columns, fp32, taps accumulated in order with separately rounded products), bilinear
+// resize to (dw, dh).  One kernel per layer: a CTA owns a TXD x TYD destination tile, stages the u8 source region
+// it depends on in shared memory (reflected at the image border), blurs horizontally only at the (up to) two source
+// columns each destination column samples, then vertically only at the two sampled rows, and combines.
+// HBM traffic: the u8 frame once per layer (L2-resident after the first layer) + 4 B per destination pixel.
 // ---------------------------------------------------------------------------------------------------
-__global__ void pyr_h_kernel(const uint8_t* __restrict__ img, size_t step, size_t fstride, int W, int H, int dw,
-                             double scale_x, int two, SmoothCoef sc, float* __restrict__ htmp, size_t hstride)
+struct PyrArgs {
+    const uint8_t* img; size_t step, fstride; int W, H;
+    int dw, dh; double sxs, sys; int two;
+    float* out; int pitch; size_t ostride;
+    int TXD, TYD, SRW, SRH;
+};
+
+__global__ void __launch_bounds__(256)
+pyr_tile_kernel(PyrArgs a, SmoothCoef sc)
 {
-    int X = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (X >= dw || y >= H) return;
-    img += (size_t)blockIdx.z * fstride;
-    htmp += (size_t)blockIdx.z * hstride;
-    int sx; float fx;
-    if (two) resize_coef(X, W, scale_x, sx, fx); else sx = X;
-    const uint8_t* row = img + (size_t)y * step;
-    const int r = sc.ksize / 2;
-    float s0 = 0.f, s1 = 0.f;
-    int sx1 = sx + 1 < W ? sx + 1 : W - 1;
-    if (sx - r >= 0 && sx1 + r < W) {
-        for (int i = 0; i < sc.ksize; i++) {
-            s0 = __fadd_rn(s0, __fmul_rn(sc.k[i], (float)row[sx + i - r]));
-            if (two) s1 = __fadd_rn(s1, __fmul_rn(sc.k[i], (float)row[sx1 + i - r]));
+    extern __shared__ __align__(16) unsigned char psm[];
+    const int TXD = a.TXD, TYD = a.TYD, SRW = a.SRW, SRH = a.SRH;
+    const int lx = 31 - __clz(TXD);                                    // TXD is a power of two
+    float2* sT = reinterpret_cast<float2*>(psm);                       // [SRH][TXD] horizontally blurred pairs
+    float* sS = reinterpret_cast<float*>(sT + (size_t)SRH * TXD);      // [SRH][SRW] source region as fp32
+    int* cS = reinterpret_cast<int*>(sS + (size_t)SRH * SRW);          // [TXD] sx, [TYD] sy
+    float* cF = reinterpret_cast<float*>(cS + TXD + TYD);              // [TXD] fx, [TYD] fy
+    int* gX = reinterpret_cast<int*>(cF + TXD + TYD);                  // [SRW] reflected source column of region col
+    const int tid = threadIdx.x, r = sc.ksize / 2;
+    const int X0 = blockIdx.x * TXD, Y0 = blockIdx.y * TYD;
+    const uint8_t* img = a.img + (size_t)blockIdx.z * a.fstride;
+    float* out = a.out + (size_t)blockIdx.z * a.ostride;
+
+    for (int i = tid; i < TXD + TYD; i += 256) {
+        int s; float f = 0.f;
+        if (i < TXD) {
+            const int X = min(X0 + i, a.dw - 1);
+            if (a.two) resize_coef(X, a.W, a.sxs, s, f); else s = X;
+        } else {
+            const int Y = min(Y0 + i - TXD, a.dh - 1);
+            if (a.two) resize_coef(Y, a.H, a.sys, s, f); else s = Y;
         }
-    } else {
-        for (int i = 0; i < sc.ksize; i++) {
-            s0 = __fadd_rn(s0, __fmul_rn(sc.k[i], (float)row[reflect101(sx + i - r, W)]));
-            if (two) s1 = __fadd_rn(s1, __fmul_rn(sc.k[i], (float)row[reflect101(sx1 + i - r, W)]));
+        cS[i] = s; cF[i] = f;
+    }
+    __syncthreads();
+    const int ox = cS[0] - r, oy = cS[TXD] - r;
+    for (int i = tid; i < SRW; i += 256) gX[i] = reflect101(ox + i, a.W);
+    __syncthreads();
+    {   // stage the source region: warp = row, lane = column
+        const int lane = tid & 31, wrp = tid >> 5;
+        for (int ry = wrp; ry < SRH; ry += 8) {
+            const uint8_t* grow = img + (size_t)reflect101(oy + ry, a.H) * a.step;
+            float* srow = sS + ry * SRW;
+            for (int rx = lane; rx < SRW; rx += 32) srow[rx] = (float)grow[gX[rx]];
         }
     }
-    if (two) reinterpret_cast<float2*>(htmp)[(size_t)y * dw + X] = make_float2(s0, s1);
-    else htmp[(size_t)y * dw + X] = s0;
+    __syncthreads();
+    // horizontal blur at the sampled columns, every staged row
+    for (int idx = tid; idx < (SRH << lx); idx += 256) {
+        const int ry = idx >> lx, tx = idx & (TXD - 1);
+        const int sx = cS[tx];
+        const float* row = sS + ry * SRW + (sx - r - ox);
+        float s0 = __fmul_rn(sc.k[0], row[0]), s1 = 0.f;
+        if (a.two) {
+            const int d1 = (sx + 1 < a.W ? sx + 1 : a.W - 1) - sx;
+            s1 = __fmul_rn(sc.k[0], row[d1]);
+            for (int i = 1; i < sc.ksize; i++) {
+                s0 = __fadd_rn(s0, __fmul_rn(sc.k[i], row[i]));
+                s1 = __fadd_rn(s1, __fmul_rn(sc.k[i], row[i + d1]));
+            }
+        } else {
+            for (int i = 1; i < sc.ksize; i++) s0 = __fadd_rn(s0, __fmul_rn(sc.k[i], row[i]));
+        }
+        sT[idx] = make_float2(s0, s1);
+    }
+    __syncthreads();
+    // vertical blur at the sampled rows + bilinear combination
+    for (int idx = tid; idx < (TYD << lx); idx += 256) {
+        const int ty = idx >> lx, tx = idx & (TXD - 1);
+        const int X = X0 + tx, Y = Y0 + ty;
+        if (X >= a.dw || Y >= a.dh) continue;
+        const int sy = cS[TXD + ty];
+        const float2* colp = sT + ((sy - r - oy) << lx) + tx;
+        float v;
+        if (a.two) {
+            const int d1 = ((sy + 1 < a.H ? sy + 1 : a.H - 1) - sy) << lx;
+            const float fx = cF[tx], fy = cF[TXD + ty];
+            const float2 p0 = colp[0], q0 = colp[d1];
+            float b00 = __fmul_rn(sc.k[0], p0.x), b01 = __fmul_rn(sc.k[0], p0.y);
+            float b10 = __fmul_rn(sc.k[0], q0.x), b11 = __fmul_rn(sc.k[0], q0.y);
+            for (int jj = 1; jj < sc.ksize; jj++) {
+                const float2 p = colp[jj << lx], q = colp[(jj << lx) + d1];
+                b00 = __fadd_rn(b00, __fmul_rn(sc.k[jj], p.x)); b01 = __fadd_rn(b01, __fmul_rn(sc.k[jj], p.y));
+                b10 = __fadd_rn(b10, __fmul_rn(sc.k[jj], q.x)); b11 = __fadd_rn(b11, __fmul_rn(sc.k[jj], q.y));
+            }
+            const float top = __fadd_rn(__fmul_rn(b00, 1.f - fx), __fmul_rn(b01, fx));
+            const float bot = __fadd_rn(__fmul_rn(b10, 1.f - fx), __fmul_rn(b11, fx));
+            v = __fadd_rn(__fmul_rn(top, 1.f - fy), __fmul_rn(bot, fy));
+        } else {
+            float s = __fmul_rn(sc.k[0], colp[0].x);
+            for (int jj = 1; jj < sc.ksize; jj++) s = __fadd_rn(s, __fmul_rn(sc.k[jj], colp[jj << lx].x));
+            v = s;
+        }
+        out[(size_t)Y * a.pitch + X] = v;
+    }
 }
 
-// pass 2: vertical blur at the two source rows each destination row samples, then the bilinear combination.
-__global__ void pyr_v_kernel(const float* __restrict__ htmp, size_t hstride, int W, int H, int dw, int dh,
-                             double scale_x, double scale_y, int two, SmoothCoef sc, float* __restrict__ out, int pitch,
-                             size_t ostride)
+// Layer 0 (no resize; OpenCV's 3-tap [1/4 1/2 1/4] presmooth): each thread produces 4 adjacent pixels from three
+// 4-byte row loads + two edge bytes per row.  Same tap order and separately rounded products as the tile kernel.
+__global__ void __launch_bounds__(256)
+pyr0_kernel(const uint8_t* __restrict__ img, size_t step, size_t fstride, int W, int H, float k0, float k1, float k2,
+            float* __restrict__ out, int pitch, size_t ostride)
 {
-    int X = blockIdx.x * blockDim.x + threadIdx.x;
-    int Y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (X >= dw || Y >= dh) return;
-    htmp += (size_t)blockIdx.z * hstride;
+    const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;       // W % 4 == 0 is guaranteed by the launcher
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= W || y >= H) return;
+    img += (size_t)blockIdx.z * fstride;
     out += (size_t)blockIdx.z * ostride;
-    const int r = sc.ksize / 2;
-    if (!two) {
-        float s = 0.f;
-        for (int j = 0; j < sc.ksize; j++)
-            s = __fadd_rn(s, __fmul_rn(sc.k[j], htmp[(size_t)reflect101(Y + j - r, H) * dw + X]));
-        out[(size_t)Y * pitch + X] = s;
-        return;
+    const int xl = x > 0 ? x - 1 : 1, xr = x + 4 < W ? x + 4 : W - 2;   // REFLECT_101
+    float hb[3][4];
+#pragma unroll
+    for (int rr = 0; rr < 3; rr++) {
+        int yy = y + rr - 1;
+        yy = yy < 0 ? 1 : (yy >= H ? H - 2 : yy);
+        const uint8_t* row = img + (size_t)yy * step;
+        const uchar4 m = *reinterpret_cast<const uchar4*>(row + x);
+        const float v[6] = {(float)row[xl], (float)m.x, (float)m.y, (float)m.z, (float)m.w, (float)row[xr]};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            hb[rr][i] = __fadd_rn(__fadd_rn(__fmul_rn(k0, v[i]), __fmul_rn(k1, v[i + 1])), __fmul_rn(k2, v[i + 2]));
     }
-    int sx, sy; float fx, fy;
-    resize_coef(X, W, scale_x, sx, fx);
-    resize_coef(Y, H, scale_y, sy, fy);
-    int sy1 = sy + 1 < H ? sy + 1 : H - 1;
-    const float2* t = reinterpret_cast<const float2*>(htmp);
-    float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
-    for (int j = 0; j < sc.ksize; j++) {
-        float2 a = t[(size_t)reflect101(sy + j - r, H) * dw + X];
-        float2 b = t[(size_t)reflect101(sy1 + j - r, H) * dw + X];
-        b00 = __fadd_rn(b00, __fmul_rn(sc.k[j], a.x)); b01 = __fadd_rn(b01, __fmul_rn(sc.k[j], a.y));
-        b10 = __fadd_rn(b10, __fmul_rn(sc.k[j], b.x)); b11 = __fadd_rn(b11, __fmul_rn(sc.k[j], b.y));
-    }
-    float top = __fadd_rn(__fmul_rn(b00, 1.f - fx), __fmul_rn(b01, fx));
-    float bot = __fadd_rn(__fmul_rn(b10, 1.f - fx), __fmul_rn(b11, fx));
-    out[(size_t)Y * pitch + X] = __fadd_rn(__fmul_rn(top, 1.f - fy), __fmul_rn(bot, fy));
+    float4 o;
+    o.x = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[0][0]), __fmul_rn(k1, hb[1][0])), __fmul_rn(k2, hb[2][0]));
+    o.y = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[0][1]), __fmul_rn(k1, hb[1][1])), __fmul_rn(k2, hb[2][1]));
+    o.z = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[0][2]), __fmul_rn(k1, hb[1][2])), __fmul_rn(k2, hb[2][2]));
+    o.w = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[0][3]), __fmul_rn(k1, hb[1][3])), __fmul_rn(k2, hb[2][3]));
+    *reinterpret_cast<float4*>(out + (size_t)y * pitch + x) = o;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -166,10 +236,10 @@ __global__ void polyexp_strict_kernel(const float* __restrict__ I, size_t istrid
             b5 = __dadd_rn(b5, __dmul_rn((double)__fadd_rn(q2[k], q2[-k]), (double)pc.g[k]));
         }
         size_t o = (size_t)y * pitch + x;
-        R[o] = (float)__dmul_rn(b3, pc.ig11);
-        R[plane + o] = (float)__dmul_rn(b2, pc.ig11);
-        R[2 * plane + o] = (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b5, pc.ig33));
-        R[3 * plane + o] = (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b4, pc.ig33));
+        reinterpret_cast<float4*>(R)[o] =
+            make_float4((float)__dmul_rn(b3, pc.ig11), (float)__dmul_rn(b2, pc.ig11),
+                        (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b5, pc.ig33)),
+                        (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b4, pc.ig33)));
         R[4 * plane + o] = (float)__dmul_rn(b6, pc.ig55);
     }
 }
@@ -284,19 +354,15 @@ polyexp_fast_kernel(const float* __restrict__ I, size_t istride, int w, int h, i
                 o0[i] = a3 * pc.ig11; o4[i] = a6 * pc.ig55;
             }
             const size_t o = (size_t)y * pitch + x;
+            float4* A = reinterpret_cast<float4*>(R) + o;
             if (x + 3 < w) {
-                *reinterpret_cast<float4*>(R + o) = make_float4(o0[0], o0[1], o0[2], o0[3]);
-                *reinterpret_cast<float4*>(R + plane + o) = make_float4(o1[0], o1[1], o1[2], o1[3]);
-                *reinterpret_cast<float4*>(R + 2 * plane + o) = make_float4(o2[0], o2[1], o2[2], o2[3]);
-                *reinterpret_cast<float4*>(R + 3 * plane + o) = make_float4(o3[0], o3[1], o3[2], o3[3]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) A[i] = make_float4(o0[i], o1[i], o2[i], o3[i]);
                 *reinterpret_cast<float4*>(R + 4 * plane + o) = make_float4(o4[0], o4[1], o4[2], o4[3]);
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; i++)
-                    if (x + i < w) {
-                        R[o + i] = o0[i]; R[plane + o + i] = o1[i]; R[2 * plane + o + i] = o2[i];
-                        R[3 * plane + o + i] = o3[i]; R[4 * plane + o + i] = o4[i];
-                    }
+                    if (x + i < w) { A[i] = make_float4(o0[i], o1[i], o2[i], o3[i]); R[4 * plane + o + i] = o4[i]; }
             }
         }
     }
@@ -305,48 +371,53 @@ polyexp_fast_kernel(const float* __restrict__ I, size_t istride, int w, int h, i
 // ---------------------------------------------------------------------------------------------------
 // updateMatrices for one pixel (Appendix A.5).  R0/R1 = 5 planes each.  Result -> m[5].
 // ---------------------------------------------------------------------------------------------------
-template <bool S>
-__device__ __forceinline__ void update_matrices_core(int x, int y, float dx, float dy, int w, int h,
-                                                     const float* __restrict__ R0, const float* __restrict__ R1,
-                                                     size_t plane, int pitch, float m[5])
+// R view of one frame: A = {c0..c3} per pixel, B = c4
+struct RView { const float4* A; const float* B; };
+__device__ __forceinline__ RView rview(const float* slot, size_t plane)
 {
-    const size_t p = (size_t)y * pitch + x;
+    return RView{reinterpret_cast<const float4*>(slot), slot + 4 * plane};
+}
+
+template <bool S>
+__device__ __forceinline__ void update_matrices_core(int x, int y, float dx, float dy, int w, int h, const RView& R0,
+                                                     const RView& R1, int pitch, float m[5])
+{
+    const int p = y * pitch + x;
     float fx = fadd<S>((float)x, dx), fy = fadd<S>((float)y, dy);
-    int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
-    fx = fsub<S>(fx, (float)x1); fy = fsub<S>(fy, (float)y1);
-    const float r0_0 = __ldg(R0 + p), r0_1 = __ldg(R0 + plane + p), r0_2 = __ldg(R0 + 2 * plane + p),
-                r0_3 = __ldg(R0 + 3 * plane + p), r0_4 = __ldg(R0 + 4 * plane + p);
+    const float flx = floorf(fx), fly = floorf(fy);
+    const int x1 = (int)flx, y1 = (int)fly;
+    fx = fsub<S>(fx, flx); fy = fsub<S>(fy, fly);
+    const float4 r0 = __ldg(R0.A + p);
+    const float r0_4 = __ldg(R0.B + p);
     float r2, r3, r4, r5, r6;
     if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-        const float a00 = fmul<S>(1.f - fx, 1.f - fy), a01 = fmul<S>(fx, 1.f - fy), a10 = fmul<S>(1.f - fx, fy),
-                    a11 = fmul<S>(fx, fy);
-        const size_t q = (size_t)y1 * pitch + x1, qd = q + pitch;
-        float v[5];
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-            const float* pl = R1 + c * plane;
-            float t = fmul<S>(a00, __ldg(pl + q));
-            t = fadd<S>(t, fmul<S>(a01, __ldg(pl + q + 1)));
-            t = fadd<S>(t, fmul<S>(a10, __ldg(pl + qd)));
-            t = fadd<S>(t, fmul<S>(a11, __ldg(pl + qd + 1)));
-            v[c] = t;
-        }
-        r2 = v[0]; r3 = v[1];
-        r4 = fmul<S>(fadd<S>(r0_2, v[2]), 0.5f);
-        r5 = fmul<S>(fadd<S>(r0_3, v[3]), 0.5f);
-        r6 = fmul<S>(fadd<S>(r0_4, v[4]), 0.25f);
+        const int q = y1 * pitch + x1;
+        const float4 t00 = __ldg(R1.A + q), t01 = __ldg(R1.A + q + 1), t10 = __ldg(R1.A + q + pitch),
+                     t11 = __ldg(R1.A + q + pitch + 1);
+        const float u00 = __ldg(R1.B + q), u01 = __ldg(R1.B + q + 1), u10 = __ldg(R1.B + q + pitch),
+                    u11 = __ldg(R1.B + q + pitch + 1);
+        const float gx = 1.f - fx, gy = 1.f - fy;
+        const float a00 = fmul<S>(gx, gy), a01 = fmul<S>(fx, gy), a10 = fmul<S>(gx, fy), a11 = fmul<S>(fx, fy);
+#define RC_BILERP(c00, c01, c10, c11) \
+    fadd<S>(fadd<S>(fadd<S>(fmul<S>(a00, c00), fmul<S>(a01, c01)), fmul<S>(a10, c10)), fmul<S>(a11, c11))
+        r2 = RC_BILERP(t00.x, t01.x, t10.x, t11.x);
+        r3 = RC_BILERP(t00.y, t01.y, t10.y, t11.y);
+        r4 = fmul<S>(fadd<S>(r0.z, RC_BILERP(t00.z, t01.z, t10.z, t11.z)), 0.5f);
+        r5 = fmul<S>(fadd<S>(r0.w, RC_BILERP(t00.w, t01.w, t10.w, t11.w)), 0.5f);
+        r6 = fmul<S>(fadd<S>(r0_4, RC_BILERP(u00, u01, u10, u11)), 0.25f);
+#undef RC_BILERP
     } else {
         r2 = r3 = 0.f;
-        r4 = r0_2; r5 = r0_3; r6 = fmul<S>(r0_4, 0.5f);
+        r4 = r0.z; r5 = r0.w; r6 = fmul<S>(r0_4, 0.5f);
     }
-    r2 = fmul<S>(fsub<S>(r0_0, r2), 0.5f);
-    r3 = fmul<S>(fsub<S>(r0_1, r3), 0.5f);
+    r2 = fmul<S>(fsub<S>(r0.x, r2), 0.5f);
+    r3 = fmul<S>(fsub<S>(r0.y, r3), 0.5f);
     r2 = fadd<S>(r2, fadd<S>(fmul<S>(r4, dy), fmul<S>(r6, dx)));
     r3 = fadd<S>(r3, fadd<S>(fmul<S>(r6, dy), fmul<S>(r5, dx)));
     if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
-        const float border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
-        float scale = __fmul_rn(__fmul_rn(__fmul_rn(x < 5 ? border[x] : 1.f, x >= w - 5 ? border[w - x - 1] : 1.f),
-                                          y < 5 ? border[y] : 1.f), y >= h - 5 ? border[h - y - 1] : 1.f);
+        // border = {0.14, 0.14, 0.4472, 0.4472, 0.4472} indexed by the distance to each edge
+        auto bw = [](int d) { return d >= 5 ? 1.f : (d < 2 ? 0.14f : 0.4472f); };
+        float scale = __fmul_rn(__fmul_rn(__fmul_rn(bw(x), bw(w - x - 1)), bw(y)), bw(h - y - 1));
         r2 = __fmul_rn(r2, scale); r3 = __fmul_rn(r3, scale); r4 = __fmul_rn(r4, scale);
         r5 = __fmul_rn(r5, scale); r6 = __fmul_rn(r6, scale);
     }
@@ -377,6 +448,19 @@ __device__ __forceinline__ float2 upsample_flow(const float* __restrict__ coarse
     return r;
 }
 
+// the same with the per-axis resize coefficients already known
+__device__ __forceinline__ float2 upsample_flow_tab(const float2* __restrict__ cf, int cw, int ch, int sx, float fx,
+                                                    int sy, float fy, float fscale)
+{
+    const int sx1 = sx + 1 < cw ? sx + 1 : cw - 1, sy1 = sy + 1 < ch ? sy + 1 : ch - 1;
+    const float2 a = __ldg(cf + sy * cw + sx), b = __ldg(cf + sy * cw + sx1);
+    const float2 c = __ldg(cf + sy1 * cw + sx), d = __ldg(cf + sy1 * cw + sx1);
+    const float gx = 1.f - fx, gy = 1.f - fy;
+    const float tx = a.x * gx + b.x * fx, ty = a.y * gx + b.y * fx;
+    const float bx = c.x * gx + d.x * fx, by = c.y * gx + d.y * fx;
+    return make_float2((tx * gy + bx * fy) * fscale, (ty * gy + by * fy) * fscale);
+}
+
 // arguments shared by the per-layer flow kernels
 struct FlowArgs {
     const float* R; size_t plane; int pitch; int w, h; int nslots, prev_slot;
@@ -402,7 +486,7 @@ __global__ void update_matrices_kernel(FlowArgs a, int mi)
     float2 f = make_float2(0.f, 0.f);
     if (a.coarse) f = upsample_flow<S>(a.coarse + (size_t)j * a.coarse_stride, a.cw, a.ch, x, y, a.sxs, a.sys, a.fscale);
     float m[5];
-    update_matrices_core<S>(x, y, f.x, f.y, w, h, a.R0(j), a.R1(j), a.plane, a.pitch, m);
+    update_matrices_core<S>(x, y, f.x, f.y, w, h, rview(a.R0(j), a.plane), rview(a.R1(j), a.plane), a.pitch, m);
     float* M = a.M + (size_t)j * a.m_stride + (size_t)mi * 5 * a.plane;
     const size_t o = (size_t)y * a.pitch + x;
 #pragma unroll
@@ -486,7 +570,7 @@ __global__ void update_flow_strict_kernel(FlowArgs a, int mi)
     }
     if (FUSE) {
         float mm[5];
-        update_matrices_core<true>(x, y, f.x, f.y, w, h, a.R0(j), a.R1(j), a.plane, a.pitch, mm);
+        update_matrices_core<true>(x, y, f.x, f.y, w, h, rview(a.R0(j), a.plane), rview(a.R1(j), a.plane), a.pitch, mm);
         float* Mo = a.M + (size_t)j * a.m_stride + (size_t)(mi ^ 1) * 5 * a.plane;
         const size_t o = (size_t)y * a.pitch + x;
 #pragma unroll
@@ -507,8 +591,8 @@ __global__ void update_flow_strict_kernel(FlowArgs a, int mi)
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int hist_key_fast(float dx, float dy);   // aggregate.cu twin, defined below
 
-template <int NT>
-__global__ void __launch_bounds__(256)
+template <int NT, bool BOX>
+__global__ void __launch_bounds__(256, 3)
 flow_layer_kernel(FlowArgs a)
 {
     constexpr int T = 32, HALO = NT, RS = T + 2 * HALO, RP = RS + 1;
@@ -516,21 +600,34 @@ flow_layer_kernel(FlowArgs a)
     __shared__ float sM[5][RS][RP];
     __shared__ float2 sF[NT > 1 ? FS * FS : 1];
     __shared__ unsigned int sH[RC_HIST_CELLS];
-    const int w = a.w, h = a.h, j = blockIdx.z, tid = threadIdx.x;
+    __shared__ unsigned short sKeys[256];      // (direction, bin) cells this CTA touched -> only those are flushed
+    __shared__ int sNKeys;
+    __shared__ int sSX[RS], sSY[RS];
+    __shared__ float sFX[RS], sFY[RS];
+    const int w = a.w, h = a.h, j = blockIdx.z, tid = threadIdx.x, pitch = a.pitch;
     const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
-    const float* R0 = a.R0(j);
-    const float* R1 = a.R1(j);
+    const RView R0 = rview(a.R0(j), a.plane), R1 = rview(a.R1(j), a.plane);
     const bool do_hist = a.hist_delta != nullptr;
-    if (do_hist) for (int i = tid; i < RC_HIST_CELLS; i += 256) sH[i] = 0;
+    if (do_hist) {
+        for (int i = tid; i < RC_HIST_CELLS; i += 256) sH[i] = 0;
+        if (tid == 0) sNKeys = 0;
+    }
+    const float2* coarse = a.coarse ? reinterpret_cast<const float2*>(a.coarse + (size_t)j * a.coarse_stride) : nullptr;
+    if (coarse) {
+        // resize coefficients of the (clamped) columns / rows of this tile's halo region, once per CTA
+        if (tid < RS) resize_coef(clampi(x0 - HALO + tid, 0, w - 1), a.cw, a.sxs, sSX[tid], sFX[tid]);
+        else if (tid < 2 * RS) resize_coef(clampi(y0 - HALO + tid - RS, 0, h - 1), a.ch, a.sys, sSY[tid - RS], sFY[tid - RS]);
+        __syncthreads();
+    }
 
-    // ---- stage 0
+    // ---- stage 0: M0 on the whole halo region
     for (int idx = tid; idx < RS * RS; idx += 256) {
         const int cy = idx / RS, cx = idx - cy * RS;
         const int x = clampi(x0 - HALO + cx, 0, w - 1), y = clampi(y0 - HALO + cy, 0, h - 1);
         float2 f = make_float2(0.f, 0.f);
-        if (a.coarse) f = upsample_flow<false>(a.coarse + (size_t)j * a.coarse_stride, a.cw, a.ch, x, y, a.sxs, a.sys, a.fscale);
+        if (coarse) f = upsample_flow_tab(coarse, a.cw, a.ch, sSX[cx], sFX[cx], sSY[cy], sFY[cy], a.fscale);
         float m[5];
-        update_matrices_core<false>(x, y, f.x, f.y, w, h, R0, R1, a.plane, a.pitch, m);
+        update_matrices_core<false>(x, y, f.x, f.y, w, h, R0, R1, pitch, m);
 #pragma unroll
         for (int c = 0; c < 5; c++) sM[c][cy][cx] = m[c];
     }
@@ -539,15 +636,16 @@ flow_layer_kernel(FlowArgs a)
     const float k0 = a.win.k[0], k1 = a.win.k[1], ps = a.win.post_scale;
 #pragma unroll
     for (int it = 0; it < NT; it++) {
+        constexpr int dummy = 0; (void)dummy;
         const int hs = HALO - (it + 1);            // halo of this iteration's output region
         const int side = T + 2 * hs, off = HALO - hs;
         const bool last = it == NT - 1;
-        // (a) blur + solve: thread = (column, run of L rows); 3x3 window slides down in registers
+        // (a) blur + solve: thread = (column, run of L rows); the 3x3 window slides down in registers
         const int runs = 256 / side, L = (side + runs - 1) / runs;
         const int col = tid % side, run = tid / side;
-        const bool active = run < runs && run * L < side;
-        float win[3][3][5];                         // [row][col][channel]
         const int r_begin = run * L, r_end = min(side, r_begin + L);
+        const bool active = run < runs && r_begin < side;
+        float win[3][3][5];                         // [row][col][channel]
         if (active) {
 #pragma unroll
             for (int rr = 0; rr < 2; rr++)
@@ -556,6 +654,7 @@ flow_layer_kernel(FlowArgs a)
 #pragma unroll
                     for (int c = 0; c < 5; c++) win[rr + 1][cc][c] = sM[c][off + r_begin - 1 + rr][off + col - 1 + cc];
         }
+#pragma unroll
         for (int i = 0; i < L; i++) {
             const int r = r_begin + i;
             const bool ok = active && r < r_end;
@@ -571,21 +670,33 @@ flow_layer_kernel(FlowArgs a)
                 float s[5];
 #pragma unroll
                 for (int c = 0; c < 5; c++) {
-                    float v0 = fmaf(win[0][0][c] + win[2][0][c], k1, win[1][0][c] * k0);
-                    float v1 = fmaf(win[0][1][c] + win[2][1][c], k1, win[1][1][c] * k0);
-                    float v2 = fmaf(win[0][2][c] + win[2][2][c], k1, win[1][2][c] * k0);
-                    s[c] = fmaf(v0 + v2, k1, v1 * k0) * ps;
+                    if (BOX) {
+                        const float v0 = win[1][0][c] + (win[0][0][c] + win[2][0][c]);
+                        const float v1 = win[1][1][c] + (win[0][1][c] + win[2][1][c]);
+                        const float v2 = win[1][2][c] + (win[0][2][c] + win[2][2][c]);
+                        s[c] = (v1 + (v0 + v2)) * ps;
+                    } else {
+                        const float v0 = fmaf(win[0][0][c] + win[2][0][c], k1, win[1][0][c] * k0);
+                        const float v1 = fmaf(win[0][1][c] + win[2][1][c], k1, win[1][1][c] * k0);
+                        const float v2 = fmaf(win[0][2][c] + win[2][2][c], k1, win[1][2][c] * k0);
+                        s[c] = fmaf(v0 + v2, k1, v1 * k0) * ps;
+                    }
                 }
                 f = solve_fast(s[0], s[1], s[2], s[3], s[4]);
             }
             if (last) {
                 const int x = x0 + col, y = y0 + r;
                 const bool in = ok && x < w && y < h;
-                if (in) reinterpret_cast<float2*>(a.out(j))[(size_t)y * w + x] = f;
+                if (in) reinterpret_cast<float2*>(a.out(j))[y * w + x] = f;
                 if (do_hist) {
                     const int key = in ? hist_key_fast(f.x, f.y) : -1;
                     const unsigned peers = __match_any_sync(0xffffffffu, key);
-                    if (key >= 0 && (int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&sH[key], __popc(peers));
+                    if (key >= 0 && (int)(__ffs(peers) - 1) == (tid & 31)) {
+                        if (atomicAdd(&sH[key], __popc(peers)) == 0) {
+                            const int slot = atomicAdd(&sNKeys, 1);
+                            if (slot < 256) sKeys[slot] = (unsigned short)key;
+                        }
+                    }
                 }
             } else if (ok) {
                 sF[r * side + col] = f;
@@ -599,7 +710,7 @@ flow_layer_kernel(FlowArgs a)
                 const int x = clampi(x0 - hs + cx, 0, w - 1), y = clampi(y0 - hs + cy, 0, h - 1);
                 const float2 f = sF[(y - (y0 - hs)) * side + (x - (x0 - hs))];
                 float m[5];
-                update_matrices_core<false>(x, y, f.x, f.y, w, h, R0, R1, a.plane, a.pitch, m);
+                update_matrices_core<false>(x, y, f.x, f.y, w, h, R0, R1, pitch, m);
 #pragma unroll
                 for (int c = 0; c < 5; c++) sM[c][off + cy][off + cx] = m[c];
             }
@@ -609,8 +720,13 @@ flow_layer_kernel(FlowArgs a)
     if (do_hist) {
         __syncthreads();
         unsigned int* dst = a.hist_delta + (size_t)j * RC_HIST_CELLS;
-        for (int i = tid; i < RC_HIST_CELLS; i += 256)
-            if (sH[i]) atomicAdd(&dst[i], sH[i]);
+        const int nk = sNKeys;
+        if (nk <= 256) {
+            if (tid < nk) { const int k = sKeys[tid]; atomicAdd(&dst[k], sH[k]); }
+        } else {
+            for (int i = tid; i < RC_HIST_CELLS; i += 256)
+                if (sH[i]) atomicAdd(&dst[i], sH[i]);
+        }
     }
 }
 
@@ -703,20 +819,40 @@ void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fs
     const int W = c->prm.w, H = c->prm.h;
     for (int k = 0; k < c->nlayers; k++) {
         Layer& L = c->layer[k];
-        const int two = !(L.w == W && L.h == H);
-        const double sx = 1.0 / ((double)L.w / (double)W), sy = 1.0 / ((double)L.h / (double)H);
-        dim3 b(32, 8);
-        {
-            dim3 g1((L.w + 31) / 32, (H + 7) / 8, nb);
-            KScope ks(c, K_PYR_H, (double)W * H * nb);
-            pyr_h_kernel<<<g1, b, 0, c->stream>>>(d_frames, step, fstride, W, H, L.w, sx, two, L.smooth, L.htmp,
-                                                 L.htmp_stride);
+        PyrArgs a;
+        a.img = d_frames; a.step = step; a.fstride = fstride; a.W = W; a.H = H; a.dw = L.w; a.dh = L.h;
+        a.two = !(L.w == W && L.h == H);
+        a.sxs = 1.0 / ((double)L.w / (double)W); a.sys = 1.0 / ((double)L.h / (double)H);
+        a.out = L.I; a.pitch = L.pitch; a.ostride = (size_t)L.pitch * L.h;
+        const int r = L.smooth.ksize / 2;
+        if (!a.two && L.smooth.ksize == 3 && W % 4 == 0 && W >= 8 && H >= 2 && step % 4 == 0 && fstride % 4 == 0 &&
+            (reinterpret_cast<size_t>(d_frames) & 3) == 0) {
+            dim3 g((W / 4 + 63) / 64, (H + 3) / 4, nb);
+            KScope ks(c, K_PYR_V, ((double)W * H + 4.0 * L.w * L.h) * nb);
+            pyr0_kernel<<<g, 256, 0, c->stream>>>(d_frames, step, fstride, W, H, L.smooth.k[0], L.smooth.k[1],
+                                                 L.smooth.k[2], L.I, L.pitch, (size_t)L.pitch * L.h);
+            launch_polyexp(c, L, nb, first_slot);
+            continue;
+        }
+        static const int cand[6][2] = {{64, 16}, {32, 16}, {32, 8}, {16, 8}, {8, 8}, {8, 4}};
+        size_t smem = 0;
+        for (int i = 0; i < 6; i++) {
+            a.TXD = cand[i][0]; a.TYD = cand[i][1];
+            a.SRW = (int)(a.sxs * (a.TXD - 1)) + 2 * r + 4; a.SRH = (int)(a.sys * (a.TYD - 1)) + 2 * r + 4;
+            a.SRW |= 1;       // odd row pitch: column-strided reads of the staged region spread over the banks
+            smem = sizeof(float2) * (size_t)a.SRH * a.TXD + 4 * (size_t)a.SRH * a.SRW + 8 * (size_t)(a.TXD + a.TYD) +
+                   4 * (size_t)a.SRW;
+            if (smem <= 100 * 1024) break;
+        }
+        static size_t configured = 0;
+        if (smem > configured && smem > 48 * 1024) {
+            cudaFuncSetAttribute(pyr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
         }
         {
-            dim3 g2((L.w + 31) / 32, (L.h + 7) / 8, nb);
-            KScope ks(c, K_PYR_V, 4.0 * L.w * L.h * nb);
-            pyr_v_kernel<<<g2, b, 0, c->stream>>>(L.htmp, L.htmp_stride, W, H, L.w, L.h, sx, sy, two, L.smooth, L.I,
-                                                 L.pitch, (size_t)L.pitch * L.h);
+            dim3 g((L.w + a.TXD - 1) / a.TXD, (L.h + a.TYD - 1) / a.TYD, nb);
+            KScope ks(c, K_PYR_V, ((k == 0 ? (double)W * H : 0.0) + 4.0 * L.w * L.h) * nb);
+            pyr_tile_kernel<<<g, 256, smem, c->stream>>>(a, L.smooth);
         }
         launch_polyexp(c, L, nb, first_slot);
     }
@@ -747,9 +883,15 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         if (fused_ok) {
             dim3 g((L.w + 31) / 32, (L.h + 31) / 32, nb);
             KScope ks(c, K_FLOW_LAYER, (a.coarse ? 50.0 : 48.0) * npx);
-            if (T == 1) flow_layer_kernel<1><<<g, 256, 0, c->stream>>>(a);
-            else if (T == 2) flow_layer_kernel<2><<<g, 256, 0, c->stream>>>(a);
-            else flow_layer_kernel<3><<<g, 256, 0, c->stream>>>(a);
+            if (!c->win.gaussian) {
+                if (T == 1) flow_layer_kernel<1, true><<<g, 256, 0, c->stream>>>(a);
+                else if (T == 2) flow_layer_kernel<2, true><<<g, 256, 0, c->stream>>>(a);
+                else flow_layer_kernel<3, true><<<g, 256, 0, c->stream>>>(a);
+            } else {
+                if (T == 1) flow_layer_kernel<1, false><<<g, 256, 0, c->stream>>>(a);
+                else if (T == 2) flow_layer_kernel<2, false><<<g, 256, 0, c->stream>>>(a);
+                else flow_layer_kernel<3, false><<<g, 256, 0, c->stream>>>(a);
+            }
             continue;
         }
         dim3 b(32, 8), g((L.w + 31) / 32, (L.h + 7) / 8, nb);
