@@ -184,6 +184,19 @@ int rc_advect(rc_ctx* ctx, const float* flow, size_t flow_step, int w, int h, fl
 int rc_streakline_step(rc_ctx* ctx, const float* flow, size_t flow_step, int w, int h, const float* emitters, int E,
                        float* vertices, int32_t* count, int cap, float dt);
 
+/* ---- entry points on the reference's own intermediate formats (used by the header-compatible C++ wrappers) ---- */
+/* counting loop of create_histogram (ripcurrents_module.cpp:94-107) on the merged polar image CV_32FC3
+ * (angle deg, mag, mag); adds into the context's cumulative counters like rc_polar_hist */
+int rc_hist_from_polar(rc_ctx* ctx, const float* polar3, size_t step, int w, int h);
+/* create_flow (ripcurrents_module.cpp:153-182): all three images are CV_32FC3, updated in place */
+int rc_create_flow(rc_ctx* ctx, float* current3, size_t cur_step, float* waterclass3, size_t wc_step,
+                   float* accumulator2_3, size_t acc2_step, int w, int h, float UPPER, float MID, float LOWER,
+                   const float UPPER2d[RC_HIST_DIRECTIONS]);
+/* create_accumulationbuffer (ripcurrents_module.cpp:189-212): accumulator/accumulator2/out CV_32FC3, outmask CV_8UC1 */
+int rc_create_accumulationbuffer(rc_ctx* ctx, float* accumulator3, size_t acc_step, const float* accumulator2_3,
+                                 size_t acc2_step, float* out3, size_t out_step, uint8_t* outmask, size_t mask_step, int w,
+                                 int h, int framecount);
+
 /* ---- fused per-frame step (what main()'s loop body does between video.read and imshow) ----------- */
 typedef struct rc_frame_result {
     int produced;                            /* 1 if a flow was produced (0 for the priming frame) */

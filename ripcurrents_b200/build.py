@@ -12,13 +12,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libripcurrents_b200.so")
-SOURCES = ["farneback.cu", "aggregate.cu", "advect.cu", "api.cu"]
+SOURCES = ["farneback.cu", "aggregate.cu", "advect.cu", "compat.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall", "-Xptxas", "-v"]
 # farneback.cu holds both arithmetic modes: its strict code is written with __fmul_rn/__fadd_rn intrinsics (never
 # contracted) and its fast code wants FMA contraction; the other files restate reference arithmetic in which every
 # product and sum rounds separately, so they are compiled with contraction off.
-EXTRA = {"farneback.cu": [], "aggregate.cu": ["-fmad=false"], "advect.cu": ["-fmad=false"], "api.cu": ["-fmad=false"]}
+EXTRA = {"farneback.cu": [], "aggregate.cu": ["-fmad=false"], "advect.cu": ["-fmad=false"], "compat.cu": ["-fmad=false"], "api.cu": ["-fmad=false"]}
 
 
 def _nvcc():
@@ -59,5 +59,27 @@ def build(force=False, verbose=False):
     return SO
 
 
+CPP = os.path.join(HERE, "cpp")
+CPP_LIB = os.path.join(LIBDIR, "libripcurrents_cpp.so")
+DEMO = os.path.join(LIBDIR, "demo_main")
+
+
+def build_cpp(force=False):
+    """Header-compatible C++ wrappers (ripcurrents.hpp / Streakline.hpp / pathlines.h) + the drop-in demo loop."""
+    so = build(force)
+    srcs = [os.path.join(CPP, f) for f in ("ripcurrents_b200.cpp", "demo_main.cpp", "ripcurrents.hpp", "Streakline.hpp",
+                                           "pathlines.h", "cv_compat.hpp")]
+    newest = max(os.path.getmtime(f) for f in srcs + [so])
+    if force or not os.path.exists(CPP_LIB) or os.path.getmtime(CPP_LIB) < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++14", "-fPIC", "-Wall", "-ffp-contract=off", "-shared", "-o", CPP_LIB,
+                               os.path.join(CPP, "ripcurrents_b200.cpp"), "-L" + LIBDIR, "-lripcurrents_b200",
+                               "-Wl,-rpath,$ORIGIN"])
+    if force or not os.path.exists(DEMO) or os.path.getmtime(DEMO) < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++14", "-Wall", "-o", DEMO, os.path.join(CPP, "demo_main.cpp"),
+                               "-L" + LIBDIR, "-lripcurrents_cpp", "-lripcurrents_b200", "-Wl,-rpath,$ORIGIN"])
+    return CPP_LIB, DEMO
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_cpp(force="--force" in sys.argv))

@@ -23,7 +23,7 @@ SYMBOLS = [
     "rc_hist_reset", "rc_polar_hist", "rc_hist_get", "rc_hist_add", "rc_hist_device", "rc_cart_to_polar",
     "rc_thresholds", "rc_accumulator_reset", "rc_classify_accumulate", "rc_accumulator_get",
     "rc_accumulator_device", "rc_window_configure", "rc_window_update", "rc_window_get", "rc_window_device",
-    "rc_subtract_mean", "rc_advect", "rc_streakline_step", "rc_process_frame",
+    "rc_subtract_mean", "rc_hist_from_polar", "rc_create_flow", "rc_create_accumulationbuffer", "rc_advect", "rc_streakline_step", "rc_process_frame",
 ]
 
 

@@ -1,0 +1,70 @@
+// Drop-in demonstration: the frame loop of the reference's legacy detector (RipCurrents_main/ripcurrents.cpp:184-439)
+// with video decoding / display removed, written against the reference's own entry points
+// (calcOpticalFlowFarneback, streamline_field, cartToPolar+merge, create_histogram, create_flow,
+// create_accumulationbuffer) as provided by ripcurrents.hpp of this repository.
+//
+//   demo_main frames.raw W H N out.bin
+// frames.raw: N frames of W*H u8.  out.bin: per processed frame { float UPPER; int histsum; float acc_sum;
+// int mask_calm; float field_sum; } -- tests/test_gpu_cpp_dropin.py compares them with the CPU oracle.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "ripcurrents.hpp"
+#include "Streakline.hpp"
+
+using namespace cv;
+
+int main(int argc, char** argv)
+{
+    if (argc < 6) { std::fprintf(stderr, "usage: %s frames.raw W H N out.bin\n", argv[0]); return 2; }
+    const int W = std::atoi(argv[2]), H = std::atoi(argv[3]), N = std::atoi(argv[4]);
+    std::vector<uchar> raw((size_t)W * H * N);
+    FILE* f = std::fopen(argv[1], "rb");
+    if (!f || std::fread(raw.data(), 1, raw.size(), f) != raw.size()) { std::fprintf(stderr, "cannot read frames\n"); return 1; }
+    std::fclose(f);
+    FILE* out_f = std::fopen(argv[5], "wb");
+    if (!out_f) return 1;
+
+    Mat accumulator = Mat::zeros(Size(W, H), CV_32FC3);                                  // ripcurrents.cpp:133
+    float LOWER = 0.2f, MID = .5f;                                                       // :142-143
+    int hist[HIST_BINS] = {0}; int histsum = 0; float UPPER = 100.0f;                    // :147-149
+    static int hist2d[HIST_DIRECTIONS][HIST_BINS]; int histsum2d[HIST_DIRECTIONS] = {0}; // :151-152
+    float UPPER2d[HIST_DIRECTIONS] = {0}, prop_above_upper[HIST_DIRECTIONS] = {0};       // :153-154
+    Mat streamlines_mat = Mat::zeros(H, W, CV_32FC2), streamlines_distance = Mat::zeros(H, W, CV_32FC1);   // :164-165
+    std::vector<Streakline> streaks;
+    streaks.push_back(Streakline(Pixel2(W * 0.3f, H * 0.4f)));
+    streaks.push_back(Streakline(Pixel2(W * 0.6f, H * 0.5f)));
+
+    Mat f2(H, W, CV_8UC1, raw.data());                                                   // preloaded frame, :184-188
+    for (int framecount = 1; framecount < N; framecount++) {                             // :194
+        Mat f1(H, W, CV_8UC1, raw.data() + (size_t)framecount * W * H);
+        Mat current;
+        rc::calcOpticalFlowFarneback(f2, f1, current, 0.5, 2, 3, 2, 15, 1.2, 0);         // :215
+        f2 = f1;                                                                          // :216
+
+        rc::streamline_field_all(streamlines_mat, streamlines_distance, current, 2, 1, UPPER);   // :229-231
+        Streakline::runAll(streaks, current);                                             // main.cpp:150-152
+
+        Mat polar;
+        rc::flowToPolar(current, polar);                                                  // :305-309
+        create_histogram(polar, hist, histsum, hist2d, histsum2d, UPPER, UPPER2d, prop_above_upper);   // :319-366
+        Mat accumulator2 = Mat::zeros(Size(W, H), CV_32FC3), waterclass = Mat::zeros(Size(W, H), CV_32FC3);   // :371-372
+        create_flow(polar, waterclass, accumulator2, UPPER, MID, LOWER, UPPER2d);         // :376-402
+        Mat out = Mat::zeros(Size(W, H), CV_32FC3), outmask = Mat::zeros(Size(W, H), CV_8UC1);   // :419-420
+        create_accumulationbuffer(accumulator, accumulator2, out, outmask, framecount + 28);    // :414-439 (offset: crosses 30)
+
+        double acc_sum = 0, field_sum = 0; int calm = 0;
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                acc_sum += accumulator.ptr<Pixel3>(y)[x].x;
+                calm += outmask.ptr<uchar>(y)[x] == 255;
+                field_sum += streamlines_distance.ptr<float>(y)[x];
+            }
+        float rec[6] = {UPPER, (float)histsum, (float)acc_sum, (float)calm, (float)field_sum,
+                        streaks[0].vertices.back().x + streaks[1].vertices.back().y};
+        std::fwrite(rec, sizeof rec, 1, out_f);
+    }
+    std::fclose(out_f);
+    return 0;
+}

@@ -1,0 +1,64 @@
+// Header-compatible replacement for the hot-path subset of the reference's RipCurrents_main/ripcurrents.hpp
+// (declarations at ripcurrents.hpp:22-25,37,39-40,48,50,52,58,77): same names, argument order and meaning, same
+// in-place / aliasing behaviour, no error channel (failures abort with a message, like the reference's CV_Assert).
+// Every function forwards to the C ABI of include/ripcurrents_b200.h on a process-wide context
+// (rc::default_context()); nothing here computes on the CPU except the 50x37-entry threshold scans that
+// create_histogram performs on the caller's own cumulative arrays.
+//
+// Additional, recommended entry points (namespace rc) batch what the reference does one pixel / one seed per call:
+// main.cpp's forEach loops become one call (INTEGRATION.md shows the 3-line diffs).
+#ifndef __RIPCURRENTS_HPP_INCLUDE__
+#define __RIPCURRENTS_HPP_INCLUDE__
+
+#include <vector>
+#include "cv_compat.hpp"
+#include "../../include/ripcurrents_b200.h"
+
+#define XDIM 640  // Dimensions to resize to (kept for source compatibility; the functions take sizes from the Mats)
+#define YDIM 480
+#define HIST_BINS 50
+#define HIST_DIRECTIONS 36
+#define HIST_RESOLUTION 20
+#define BUFFER_FRAME 300
+#define GRID_COUNT 30
+
+typedef cv::Point3_<uchar> Pixelc;
+typedef cv::Point_<float> Pixel2;
+typedef cv::Point3_<float> Pixel3;
+
+namespace rc {
+rc_ctx* default_context();                 // created on first use on device RC_B200_DEVICE (default 0)
+void set_default_device(int device);       // before first use
+// cv::calcOpticalFlowFarneback replacement (ripcurrents.cpp:215, main.cpp:264,609,742,961,1119,1481)
+void calcOpticalFlowFarneback(const cv::Mat& prev, const cv::Mat& next, cv::Mat& flow, double pyr_scale, int levels,
+                              int winsize, int iterations, int poly_n, double poly_sigma, int flags);
+// ripcurrents.cpp:305-309: split + cartToPolar(deg) + merge -> CV_32FC3 (angle, mag, mag)
+void flowToPolar(const cv::Mat& flow, cv::Mat& polar);
+// whole-image forms of the per-pixel / per-seed loops
+void streamline_field_all(cv::Mat& streamlines_mat, cv::Mat& streamlines_distance, const cv::Mat& flow, float dt,
+                          int iterations, float UPPER);                                    // ripcurrents.cpp:229-231
+void streamlines_all(Pixel2* pts, int n, const cv::Mat& flow, float dt, int iterations, float UPPER, int variant);
+void window_average(std::vector<cv::Mat>& buffer, int& currentBuffer, const cv::Mat& flow, cv::Mat& average); // main.cpp:1143-1153
+}  // namespace rc
+
+void streamline_field(Pixel2* pt, float* distancetraveled, int xoffset, int yoffset, cv::Mat flow, float dt,
+                      int iterations, float UPPER, float prop_above_upper[HIST_DIRECTIONS]);
+void streamline(Pixel2* pt, cv::Scalar color, cv::Mat flow, cv::Mat overlay, float dt, int iterations, float UPPER,
+                float prop_above_upper[HIST_DIRECTIONS]);
+void streamline_2(Pixel2* pt, cv::Scalar color, cv::Mat flow, cv::Mat overlay, float dt, int iterations, float UPPER,
+                  float prop_above_upper[HIST_DIRECTIONS]);
+void streamline_3(Pixel2* pt, cv::Scalar color, cv::Mat flow, cv::Mat overlay, float dt, int iterations, float UPPER,
+                  float prop_above_upper[HIST_DIRECTIONS]);
+void get_streamlines(cv::Mat& streamout, cv::Mat& streamoverlay_color, cv::Mat& streamoverlay, int streamlines,
+                     Pixel2 streampt[], int framecount, int totalframes, cv::Mat& current, float UPPER,
+                     float prop_above_upper[]);
+void create_histogram(cv::Mat current, int hist[HIST_BINS], int& histsum, int hist2d[HIST_DIRECTIONS][HIST_BINS],
+                      int histsum2d[HIST_DIRECTIONS], float& UPPER, float UPPER2d[HIST_DIRECTIONS],
+                      float prop_above_upper[HIST_DIRECTIONS]);
+void create_flow(cv::Mat current, cv::Mat waterclass, cv::Mat accumulator2, float UPPER, float MID, float LOWER,
+                 float UPPER2d[HIST_DIRECTIONS]);
+void create_accumulationbuffer(cv::Mat& accumulator, cv::Mat accumulator2, cv::Mat& out, cv::Mat outmask, int framecount);
+void get_delta(Pixel2* pt, int xoffset, int yoffset, cv::Mat flow, float dt, float UPPER);
+void subtructAverage(cv::Mat& current);
+
+#endif

@@ -943,6 +943,99 @@ int rc_streakline_step(rc_ctx* c, const float* flow, size_t flow_step, int w, in
     return RC_OK;
 }
 
+// ---- reference intermediate formats (compat.cu) ------------------------------------------------------------------
+// stages `bytes` of a host image into (*scratch), or passes a device pointer through
+static int stage3(rc_ctx* c, const void* p, size_t step, size_t row_bytes, int h, void** scratch, size_t* cap, void** d,
+                  size_t* d_step)
+{
+    if (is_device_ptr(p)) { *d = const_cast<void*>(p); *d_step = step; return RC_OK; }
+    int rc = ensure(c, scratch, cap, row_bytes * h); if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpy2DAsync(*scratch, row_bytes, p, step, row_bytes, h, cudaMemcpyHostToDevice, c->stream));
+    *d = *scratch; *d_step = row_bytes;
+    return RC_OK;
+}
+
+int rc_hist_from_polar(rc_ctx* c, const float* polar3, size_t step, int w, int h)
+{
+    if (!c || !polar3 || w < 1 || h < 1 || step < (size_t)w * 12) return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    int rc = ensure_aggregate(c); if (rc) return rc;
+    void* d; size_t ds;
+    rc = stage3(c, polar3, step, (size_t)w * 12, h, &c->d_tmp, &c->d_tmp_cap, &d, &ds); if (rc) return rc;
+    rc_launch_hist_polar(c, reinterpret_cast<const float*>(d), ds, w, h, c->d_hist2d);
+    CHECK_LAUNCH(c);
+    if (!is_device_ptr(polar3)) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return RC_OK;
+}
+
+int rc_create_flow(rc_ctx* c, float* cur, size_t cstep, float* wc, size_t wstep, float* acc2, size_t astep, int w, int h,
+                   float UPPER, float MID, float LOWER, const float* UPPER2d)
+{
+    if (!c || !cur || !wc || !acc2 || !UPPER2d || w < 1 || h < 1) return RC_ERR_INVALID;
+    if (cstep < (size_t)w * 12 || wstep < (size_t)w * 12 || astep < (size_t)w * 12) return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    const bool dev = is_device_ptr(cur);
+    if (dev != is_device_ptr(wc) || dev != is_device_ptr(acc2))
+        return fail(c, RC_ERR_INVALID, "current / waterclass / accumulator2 must all be host or all be device%s");
+    const size_t rb = (size_t)w * 12, img = rb * h;
+    int rc = ensure_aggregate(c); if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_thr + 1, UPPER2d, sizeof(float) * RC_HIST_DIRECTIONS,
+                                is_device_ptr(UPPER2d) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    float *dc = cur, *dw = wc, *da = acc2; size_t sc = cstep, sw = wstep, sa = astep;
+    if (!dev) {
+        rc = ensure(c, &c->d_tmp2, &c->d_tmp2_cap, 3 * img); if (rc) return rc;
+        char* base = reinterpret_cast<char*>(c->d_tmp2);
+        dc = reinterpret_cast<float*>(base); dw = reinterpret_cast<float*>(base + img); da = reinterpret_cast<float*>(base + 2 * img);
+        CUDA_TRY(c, cudaMemcpy2DAsync(dc, rb, cur, cstep, rb, h, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpy2DAsync(dw, rb, wc, wstep, rb, h, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpy2DAsync(da, rb, acc2, astep, rb, h, cudaMemcpyHostToDevice, c->stream));
+        sc = sw = sa = rb;
+    }
+    rc_launch_create_flow(c, dc, sc, dw, sw, da, sa, w, h, UPPER, MID, LOWER, c->d_thr + 1);
+    CHECK_LAUNCH(c);
+    if (!dev) {
+        CUDA_TRY(c, cudaMemcpy2DAsync(cur, cstep, dc, rb, rb, h, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpy2DAsync(wc, wstep, dw, rb, rb, h, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpy2DAsync(acc2, astep, da, rb, rb, h, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    return RC_OK;
+}
+
+int rc_create_accumulationbuffer(rc_ctx* c, float* acc, size_t astep, const float* acc2, size_t a2step, float* out,
+                                 size_t ostep, uint8_t* mask, size_t mstep, int w, int h, int framecount)
+{
+    if (!c || !acc || !acc2 || !out || !mask || w < 1 || h < 1) return RC_ERR_INVALID;
+    if (astep < (size_t)w * 12 || a2step < (size_t)w * 12 || ostep < (size_t)w * 12 || mstep < (size_t)w) return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    const bool dev = is_device_ptr(acc);
+    if (dev != is_device_ptr(acc2) || dev != is_device_ptr(out) || dev != is_device_ptr(mask))
+        return fail(c, RC_ERR_INVALID, "accumulator / accumulator2 / out / outmask must all be host or all be device%s");
+    const size_t rb = (size_t)w * 12, img = rb * h;
+    float *da = acc, *do_ = out; const float* da2 = acc2; uint8_t* dm = mask;
+    size_t sa = astep, sa2 = a2step, so = ostep, sm = mstep;
+    if (!dev) {
+        int rc = ensure(c, &c->d_tmp2, &c->d_tmp2_cap, 3 * img + (size_t)w * h + 64); if (rc) return rc;
+        char* base = reinterpret_cast<char*>(c->d_tmp2);
+        da = reinterpret_cast<float*>(base); float* d2 = reinterpret_cast<float*>(base + img);
+        do_ = reinterpret_cast<float*>(base + 2 * img); dm = reinterpret_cast<uint8_t*>(base + 3 * img);
+        CUDA_TRY(c, cudaMemcpy2DAsync(da, rb, acc, astep, rb, h, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpy2DAsync(d2, rb, acc2, a2step, rb, h, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpy2DAsync(do_, rb, out, ostep, rb, h, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpy2DAsync(dm, w, mask, mstep, w, h, cudaMemcpyHostToDevice, c->stream));
+        da2 = d2; sa = sa2 = so = rb; sm = w;
+    }
+    rc_launch_accumulate(c, da, sa, da2, sa2, do_, so, dm, sm, w, h, framecount);
+    CHECK_LAUNCH(c);
+    if (!dev) {
+        CUDA_TRY(c, cudaMemcpy2DAsync(acc, astep, da, rb, rb, h, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpy2DAsync(out, ostep, do_, rb, rb, h, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpy2DAsync(mask, mstep, dm, w, w, h, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    return RC_OK;
+}
+
 // ---- fused per-frame / per-batch step -------------------------------------------------------------------------
 int rc_submit_frames(rc_ctx* c, const uint8_t* frames, size_t step, size_t frame_stride, int count, int framecount0,
                      uint8_t* outmasks, size_t mask_stride, rc_frame_result* results)

@@ -1,0 +1,101 @@
+// Kernels behind the header-compatible C++ entry points (ripcurrents_b200/cpp) that take the reference's own
+// intermediate formats: the merged polar image CV_32FC3 (angle, mag, mag) of ripcurrents.cpp:305-309 and the
+// CV_32FC3 accumulator / class images of ripcurrents.cpp:371-439.  The device-resident pipeline (rc_process_frames)
+// never materialises these; they exist so that create_histogram / create_flow / create_accumulationbuffer can be
+// swapped in one at a time.  Compiled with -fmad=false.
+#include "rc_internal.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+hist_polar_kernel(const float* __restrict__ polar, size_t step, int w, int h, unsigned long long* __restrict__ hist2d)
+{
+    __shared__ unsigned int sh[RC_HIST_CELLS];
+    for (int i = threadIdx.x; i < RC_HIST_CELLS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const size_t n = (size_t)w * h, stride = (size_t)gridDim.x * blockDim.x;
+    const size_t nround = (n + stride - 1) / stride * stride;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        int key = -1;
+        if (i < n) {
+            const size_t y = i / w, x = i - y * w;
+            const float* p = reinterpret_cast<const float*>(reinterpret_cast<const char*>(polar) + y * step) + 3 * x;
+            const int bin = (int)(p[1] * (float)RC_HIST_RESOLUTION);                       // ripcurrents.cpp:323
+            const int dir = (int)__fdiv_rn(p[0] * (float)RC_HIST_DIRECTIONS, 360.f);        // ripcurrents.cpp:324
+            if (bin < RC_HIST_BINS && bin >= 0 && dir >= 0 && dir < RC_HIST_ROWS) key = dir * RC_HIST_BINS + bin;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[key], __popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RC_HIST_CELLS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist2d[i], (unsigned long long)sh[i]);
+}
+
+// create_flow (ripcurrents_module.cpp:153-182): classes, accumulator2.x += 1, display rescale of `current`
+__global__ void create_flow_kernel(float* __restrict__ cur, size_t cstep, float* __restrict__ wc, size_t wstep,
+                                   float* __restrict__ acc2, size_t astep, int w, int h, float UPPER, float MID,
+                                   float LOWER, const float* __restrict__ upper2d)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float* p = reinterpret_cast<float*>(reinterpret_cast<char*>(cur) + (size_t)y * cstep) + 3 * x;
+    float* c = reinterpret_cast<float*>(reinterpret_cast<char*>(wc) + (size_t)y * wstep) + 3 * x;
+    float* a = reinterpret_cast<float*>(reinterpret_cast<char*>(acc2) + (size_t)y * astep) + 3 * x;
+    int angle = (int)__fdiv_rn(p[0] * (float)RC_HIST_DIRECTIONS, 360.f);
+    const float val = p[2];
+    if (val > UPPER) { c[0] = .5f; a[0] = a[0] + 1.f; }
+    else if (val > MID) c[2] = 1.f;
+    else if (val > LOWER) c[2] = .5f;
+    else c[1] = .5f;
+    angle = angle < 0 ? 0 : (angle >= RC_HIST_DIRECTIONS ? RC_HIST_DIRECTIONS - 1 : angle);   // reference: UB for 36
+    const float z = __fdiv_rn(val, upper2d[angle]);
+    p[2] = z;
+    p[1] = z > 1.f ? 1.f : .7f;
+}
+
+// create_accumulationbuffer (ripcurrents_module.cpp:189-212)
+__global__ void accumulate_kernel(float* __restrict__ acc, size_t astep, const float* __restrict__ acc2, size_t a2step,
+                                  float* __restrict__ out, size_t ostep, unsigned char* __restrict__ mask, size_t mstep,
+                                  int w, int h, int framecount)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float* a = reinterpret_cast<float*>(reinterpret_cast<char*>(acc) + (size_t)y * astep) + 3 * x;
+    const float* a2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(acc2) + (size_t)y * a2step) + 3 * x;
+    float* o = reinterpret_cast<float*>(reinterpret_cast<char*>(out) + (size_t)y * ostep) + 3 * x;
+    if (framecount > 30) { a[0] = a2[0] + a[0]; a[1] = a2[1] + a[1]; a[2] = a2[2] + a[2]; }
+    const int val = (int)a[0];
+    if ((double)val > .1 * framecount) {
+        if ((double)val < .2 * framecount) o[2] = 1.f; else o[0] = 1.f;
+    } else {
+        o[1] = .5f;
+        mask[(size_t)y * mstep + x] = 255;
+    }
+}
+
+}  // namespace
+
+void rc_launch_hist_polar(rc_ctx* c, const float* polar, size_t step, int w, int h, unsigned long long* hist2d)
+{
+    const size_t n = (size_t)w * h;
+    size_t g = (n + 255) / 256; if (g > 148 * 4) g = 148 * 4;
+    KScope ks(c, K_POLAR_HIST, 12.0 * n);
+    hist_polar_kernel<<<(unsigned)g, 256, 0, c->stream>>>(polar, step, w, h, hist2d);
+}
+
+void rc_launch_create_flow(rc_ctx* c, float* cur, size_t cstep, float* wc, size_t wstep, float* acc2, size_t astep, int w,
+                           int h, float UPPER, float MID, float LOWER, const float* d_upper2d)
+{
+    dim3 b(32, 8), g((w + 31) / 32, (h + 7) / 8);
+    KScope ks(c, K_MISC, 48.0 * w * h);
+    create_flow_kernel<<<g, b, 0, c->stream>>>(cur, cstep, wc, wstep, acc2, astep, w, h, UPPER, MID, LOWER, d_upper2d);
+}
+
+void rc_launch_accumulate(rc_ctx* c, float* acc, size_t astep, const float* acc2, size_t a2step, float* out, size_t ostep,
+                          unsigned char* mask, size_t mstep, int w, int h, int framecount)
+{
+    dim3 b(32, 8), g((w + 31) / 32, (h + 7) / 8);
+    KScope ks(c, K_MISC, 49.0 * w * h);
+    accumulate_kernel<<<g, b, 0, c->stream>>>(acc, astep, acc2, a2step, out, ostep, mask, mstep, w, h, framecount);
+}

@@ -194,6 +194,13 @@ void rc_launch_window_update(rc_ctx* c, const float* flow, size_t flow_step, int
                              int W);
 void rc_launch_subtract_mean(rc_ctx* c, float* flow, size_t flow_step, int w, int h, double* d_sums);
 
+// ---- compat.cu -------------------------------------------------------------------------------------
+void rc_launch_hist_polar(rc_ctx* c, const float* polar, size_t step, int w, int h, unsigned long long* hist2d);
+void rc_launch_create_flow(rc_ctx* c, float* cur, size_t cstep, float* wc, size_t wstep, float* acc2, size_t astep, int w,
+                           int h, float UPPER, float MID, float LOWER, const float* d_upper2d);
+void rc_launch_accumulate(rc_ctx* c, float* acc, size_t astep, const float* acc2, size_t a2step, float* out, size_t ostep,
+                          unsigned char* mask, size_t mstep, int w, int h, int framecount);
+
 // ---- advect.cu -------------------------------------------------------------------------------------
 void rc_launch_advect(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float* seeds, size_t n, float dt,
                       int iterations, float upper, int variant, float* dist, const int32_t* home);
