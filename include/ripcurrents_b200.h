@@ -70,6 +70,15 @@ extern "C" {
 
 typedef struct rc_ctx rc_ctx;
 
+/* per-frame record returned by the fused / batched aggregation calls */
+typedef struct rc_frame_result {
+    int produced;                            /* 1 if a flow was produced (0 for the priming frame) */
+    float UPPER;
+    float UPPER2d[RC_HIST_DIRECTIONS];
+    float prop_above_upper[RC_HIST_DIRECTIONS];
+    int64_t histsum;
+} rc_frame_result;
+
 /* ---- library / context ------------------------------------------------------------------------ */
 int rc_version(void);
 const char* rc_error_string(int code);
@@ -184,6 +193,17 @@ int rc_advect(rc_ctx* ctx, const float* flow, size_t flow_step, int w, int h, fl
 int rc_streakline_step(rc_ctx* ctx, const float* flow, size_t flow_step, int w, int h, const float* emitters, int E,
                        float* vertices, int32_t* count, int cap, float dt);
 
+/* ---- one stream sharded by frame pair across ranks --------------------------------------
+ * The flow of a pair depends only on its two frames, but thresholds at frame t need the counts of ALL frames <= t.
+ * Each rank: rc_flow_push_batch(its block) -> rc_batch_hist (per-frame counts of its last nb flows) -> the caller
+ * all-gathers the counts, adds those of all EARLIER frames with rc_hist_add -> rc_aggregate_last (exact per-frame
+ * thresholds, classification into this rank's accumulator) -> all-reduce(SUM) of rc_accumulator_device (integer-
+ * valued, exact in any order) -> rc_accumulator_mask at the reporting point.  The sliding-window mean needs the flows
+ * in order and is not available in this mode. */
+int rc_batch_hist(rc_ctx* ctx, int nb, int64_t* deltas /* nb * RC_HIST_ROWS * RC_HIST_BINS, host or device */);
+int rc_aggregate_last(rc_ctx* ctx, int nb, int framecount0, rc_frame_result* results /* nb records or NULL */);
+int rc_accumulator_mask(rc_ctx* ctx, int framecount, uint8_t* outmask /* w*h u8 */);
+
 /* ---- entry points on the reference's own intermediate formats (used by the header-compatible C++ wrappers) ---- */
 /* counting loop of create_histogram (ripcurrents_module.cpp:94-107) on the merged polar image CV_32FC3
  * (angle deg, mag, mag); adds into the context's cumulative counters like rc_polar_hist */
@@ -198,13 +218,7 @@ int rc_create_accumulationbuffer(rc_ctx* ctx, float* accumulator3, size_t acc_st
                                  int h, int framecount);
 
 /* ---- fused per-frame step (what main()'s loop body does between video.read and imshow) ----------- */
-typedef struct rc_frame_result {
-    int produced;                            /* 1 if a flow was produced (0 for the priming frame) */
-    float UPPER;
-    float UPPER2d[RC_HIST_DIRECTIONS];
-    float prop_above_upper[RC_HIST_DIRECTIONS];
-    int64_t histsum;
-} rc_frame_result;
+
 /* rc_flow_push + rc_polar_hist + rc_thresholds + rc_classify_accumulate (+ rc_window_update when a window is
  * configured) for one new frame, on the device, in stream order.  outmask (w*h u8) and result may be NULL;
  * when both are NULL nothing is copied back and the call does not synchronise. */

@@ -23,7 +23,7 @@ SYMBOLS = [
     "rc_hist_reset", "rc_polar_hist", "rc_hist_get", "rc_hist_add", "rc_hist_device", "rc_cart_to_polar",
     "rc_thresholds", "rc_accumulator_reset", "rc_classify_accumulate", "rc_accumulator_get",
     "rc_accumulator_device", "rc_window_configure", "rc_window_update", "rc_window_get", "rc_window_device",
-    "rc_subtract_mean", "rc_hist_from_polar", "rc_create_flow", "rc_create_accumulationbuffer", "rc_advect", "rc_streakline_step", "rc_process_frame",
+    "rc_subtract_mean", "rc_batch_hist", "rc_aggregate_last", "rc_accumulator_mask", "rc_hist_from_polar", "rc_create_flow", "rc_create_accumulationbuffer", "rc_advect", "rc_streakline_step", "rc_process_frame",
 ]
 
 
@@ -333,6 +333,22 @@ class Context:
                           C.byref(results) if results is not None else None))
         return rc, results
 
+    def batch_hist(self, nb):
+        deltas = np.zeros((nb, HIST_ROWS, HIST_BINS), np.int64)
+        self._chk(self.lib.rc_batch_hist(self.h, C.c_int(nb), _ptr(deltas)))
+        return deltas
+
+    def aggregate_last(self, nb, framecount0, want_results=True):
+        res = (FrameResult * nb)() if want_results else None
+        self._chk(self.lib.rc_aggregate_last(self.h, C.c_int(nb), C.c_int(framecount0),
+                                             C.byref(res) if res is not None else None))
+        return res
+
+    def accumulator_mask(self, framecount):
+        mask = np.empty((self.h_img, self.w), np.uint8)
+        self._chk(self.lib.rc_accumulator_mask(self.h, C.c_int(framecount), _ptr(mask)))
+        return mask
+
     def wait(self):
         self._chk(self.lib.rc_wait(self.h))
 
@@ -340,8 +356,23 @@ class Context:
 _cudart = None
 
 
+def _memcpy_h2d(dev_ptr, src):
+    """Test helper: numpy -> device copy."""
+    _load_cudart()
+    rc = _cudart.cudaMemcpy(C.c_void_p(dev_ptr), C.c_void_p(src.ctypes.data), C.c_size_t(src.nbytes), C.c_int(1))
+    if rc != 0:
+        raise RcError("cudaMemcpy H2D failed: %d" % rc)
+
+
 def _memcpy_d2h(dst, dev_ptr):
-    """Test helper: device -> numpy copy through the CUDA runtime the library was linked with (torch-free)."""
+    """Test helper: device -> numpy copy through the CUDA runtime (torch-free)."""
+    _load_cudart()
+    rc = _cudart.cudaMemcpy(C.c_void_p(dst.ctypes.data), C.c_void_p(dev_ptr), C.c_size_t(dst.nbytes), C.c_int(2))
+    if rc != 0:
+        raise RcError("cudaMemcpy D2H failed: %d" % rc)
+
+
+def _load_cudart():
     global _cudart
     if _cudart is None:
         for name in ("libcudart.so.12", "libcudart.so", "/usr/local/cuda/lib64/libcudart.so"):
@@ -352,6 +383,3 @@ def _memcpy_d2h(dst, dev_ptr):
                 continue
         if _cudart is None:
             raise RcError("libcudart not found")
-    rc = _cudart.cudaMemcpy(C.c_void_p(dst.ctypes.data), C.c_void_p(dev_ptr), C.c_size_t(dst.nbytes), C.c_int(2))
-    if rc != 0:
-        raise RcError("cudaMemcpy D2H failed: %d" % rc)

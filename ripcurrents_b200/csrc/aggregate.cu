@@ -298,6 +298,19 @@ __global__ void sub_mean_kernel(float* __restrict__ flow, size_t flow_step, int 
     }
 }
 
+__global__ void widen_counts_kernel(const unsigned int* __restrict__ in, long long* __restrict__ out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (long long)in[i];
+}
+
+// outmask of ripcurrents.cpp:424-439 from the accumulator alone (reporting point of a sharded stream)
+__global__ void acc_mask_kernel(const float* __restrict__ acc, size_t n, double lo, uint8_t* __restrict__ mask)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mask[i] = ((double)(int)acc[i] > lo) ? 0 : 255;
+}
+
 int grid_for(size_t n, int block, int per_sm)
 {
     size_t g = (n + block - 1) / block;
@@ -350,6 +363,18 @@ void rc_launch_classify_batch(rc_ctx* c, const ClassifyBatch& cb, int w, int h, 
     KScope ks(c, K_CLASSIFY, ((8.0 + (masks ? 1.0 : 0.0)) * cb.nb + 8.0 * nold + 8.0 + (avg ? 16.0 : 0.0)) * n);
     classify_batch_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, c->stream>>>(cb, n4, n, thr_batch, framecount0, acc, masks,
                                                                               avg, inv);
+}
+
+void rc_launch_widen_counts(rc_ctx* c, const unsigned int* in, long long* out, size_t n)
+{
+    KScope ks(c, K_MISC, 12.0 * n);
+    widen_counts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(in, out, n);
+}
+
+void rc_launch_acc_mask(rc_ctx* c, const float* acc, size_t n, int framecount, uint8_t* mask)
+{
+    KScope ks(c, K_MISC, 5.0 * n);
+    acc_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(acc, n, .1 * framecount, mask);
 }
 
 void rc_launch_window_update(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float* slot, float* avg, int W)

@@ -943,6 +943,71 @@ int rc_streakline_step(rc_ctx* c, const float* flow, size_t flow_step, int w, in
     return RC_OK;
 }
 
+// ---- two-phase aggregation for a stream sharded by frame pair ---------------------------
+int rc_batch_hist(rc_ctx* c, int nb, int64_t* deltas)
+{
+    if (!c || !deltas) return RC_ERR_INVALID;
+    if (!c->configured) return fail(c, RC_ERR_STATE, "rc_flow_configure has not been called%s");
+    if (nb < 1 || nb > c->B || nb > c->pairs_done) return fail(c, RC_ERR_INVALID, "nb must be in [1, min(max_batch, flows produced)]%s");
+    cudaSetDevice(c->device);
+    int rc = ensure_aggregate(c); if (rc) return rc;
+    float* f[RC_MAX_BATCH];
+    for (int j = 0; j < nb; j++) f[j] = ring_slot(c, c->pairs_done - nb + j);
+    rc_launch_hist_of_flows(c, f, nb, c->prm.w, c->prm.h, c->d_hist_delta);
+    const size_t n = (size_t)nb * RC_HIST_CELLS;
+    const bool dev = is_device_ptr(deltas);
+    long long* d_out = reinterpret_cast<long long*>(deltas);
+    if (!dev) { rc = ensure(c, &c->d_tmp2, &c->d_tmp2_cap, n * 8); if (rc) return rc; d_out = reinterpret_cast<long long*>(c->d_tmp2); }
+    rc_launch_widen_counts(c, c->d_hist_delta, d_out, n);
+    CHECK_LAUNCH(c);
+    if (!dev) {
+        CUDA_TRY(c, cudaMemcpyAsync(deltas, d_out, n * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    return RC_OK;
+}
+
+int rc_aggregate_last(rc_ctx* c, int nb, int framecount0, rc_frame_result* results)
+{
+    if (!c) return RC_ERR_INVALID;
+    if (!c->configured) return fail(c, RC_ERR_STATE, "rc_flow_configure has not been called%s");
+    if (nb < 1 || nb > c->B || nb > c->pairs_done) return fail(c, RC_ERR_INVALID, "nb must be in [1, min(max_batch, flows produced)]%s");
+    cudaSetDevice(c->device);
+    const int w = c->prm.w, h = c->prm.h;
+    int rc = ensure_aggregate(c); if (rc) return rc;
+    rc = ensure_accumulator(c, w, h); if (rc) return rc;
+    // uses the per-frame counts left in d_hist_delta by rc_batch_hist(nb)
+    rc_launch_thresholds_batch(c, c->d_hist2d, c->d_hist_delta, nb, c->d_thr_batch[0], c->d_thr);
+    ClassifyBatch cb;
+    cb.nb = nb;
+    for (int j = 0; j < nb; j++) { cb.flow[j] = ring_slot(c, c->pairs_done - nb + j); cb.old[j] = nullptr; }
+    rc_launch_classify_batch(c, cb, w, h, c->d_thr_batch[0], framecount0, c->d_acc, nullptr, nullptr, 0);
+    CHECK_LAUNCH(c);
+    if (results) {
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_thr[0], c->d_thr_batch[0], sizeof(float) * RC_THR_FLOATS * nb, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        fill_results(c->h_thr[0], nb, 0, nb, results);
+    }
+    return RC_OK;
+}
+
+int rc_accumulator_mask(rc_ctx* c, int framecount, uint8_t* outmask)
+{
+    if (!c || !outmask) return RC_ERR_INVALID;
+    if (!c->d_acc) return fail(c, RC_ERR_STATE, "no accumulator yet%s");
+    cudaSetDevice(c->device);
+    const size_t n = (size_t)c->acc_w * c->acc_h;
+    const bool dev = is_device_ptr(outmask);
+    uint8_t* d = dev ? outmask : c->d_cls;
+    rc_launch_acc_mask(c, c->d_acc, n, framecount, d);
+    CHECK_LAUNCH(c);
+    if (!dev) {
+        CUDA_TRY(c, cudaMemcpyAsync(outmask, d, n, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    return RC_OK;
+}
+
 // ---- reference intermediate formats (compat.cu) ------------------------------------------------------------------
 // stages `bytes` of a host image into (*scratch), or passes a device pointer through
 static int stage3(rc_ctx* c, const void* p, size_t step, size_t row_bytes, int h, void** scratch, size_t* cap, void** d,

@@ -15,6 +15,7 @@
 // full 32-byte sectors; the structure matrices M of the unfused path are 5 fp32 planes; flow is interleaved float2
 // (CV_32FC2, the output format).  Every array has a leading batch dimension: one
 // launch processes all frame pairs of a batch (blockIdx.z), which is what fills 148 SMs on the small pyramid layers.
+#include <string.h>
 #include "rc_internal.h"
 
 namespace {
@@ -856,6 +857,21 @@ void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fs
         }
         launch_polyexp(c, L, nb, first_slot);
     }
+}
+
+// per-frame direction/speed counts of nb dense w*h flows (device pointers) -> delta[nb][RC_HIST_CELLS]
+void rc_launch_hist_of_flows(rc_ctx* c, float* const* flows, int nb, int w, int h, unsigned int* delta)
+{
+    FlowArgs a;
+    memset(&a, 0, sizeof a);
+    a.flow = nullptr;
+    for (int j = 0; j < nb; j++) a.flow_dst[j] = flows[j];
+    a.hist_delta = delta;
+    const int n = w * h;
+    int gx = (n + 255) / 256; if (gx > 148 * 4) gx = 148 * 4;
+    cudaMemsetAsync(delta, 0, sizeof(unsigned int) * RC_HIST_CELLS * nb, c->stream);
+    KScope ks(c, K_POLAR_HIST, 8.0 * n * nb);
+    hist_batch_kernel<<<dim3(gx, nb), 256, 0, c->stream>>>(a, n);
 }
 
 void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_host, unsigned int* hist_delta)

@@ -174,6 +174,8 @@ void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fs
 // goes to flow_dst[j]; hist_delta (may be null) receives per-pair direction/speed counts [nb][RC_HIST_CELLS].
 void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_host, unsigned int* hist_delta);
 
+void rc_launch_hist_of_flows(rc_ctx* c, float* const* flows, int nb, int w, int h, unsigned int* delta);
+
 // ---- aggregate.cu ----------------------------------------------------------------------------------
 void rc_launch_polar_hist(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, unsigned long long* hist2d);
 void rc_launch_cart_to_polar(rc_ctx* c, const float* flow, size_t n, float* mag, float* ang);
@@ -190,6 +192,8 @@ struct ClassifyBatch {
 };
 void rc_launch_classify_batch(rc_ctx* c, const ClassifyBatch& cb, int w, int h, const float* thr_batch, int framecount0,
                               float* acc, uint8_t* masks, float* avg, int W);
+void rc_launch_widen_counts(rc_ctx* c, const unsigned int* in, long long* out, size_t n);
+void rc_launch_acc_mask(rc_ctx* c, const float* acc, size_t n, int framecount, uint8_t* mask);
 void rc_launch_window_update(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float* slot, float* avg,
                              int W);
 void rc_launch_subtract_mean(rc_ctx* c, float* flow, size_t flow_step, int w, int h, double* d_sums);

@@ -219,3 +219,41 @@ def test_submit_async_matches_sync(ctx):
     assert got == rres
     assert np.array_equal(masks[1:12], rmasks[1:12])
     c.close()
+
+
+def test_sharded_two_phase_matches_sequential(oracle):
+    """Frame-pair sharding on the C ABI (rc_batch_hist / rc_hist_add / rc_aggregate_last / rc_accumulator_mask): two
+    'ranks' (two contexts on this GPU, run one after the other) reproduce the sequential per-frame thresholds, the
+    total counts and -- after summing their accumulators, which is what the NCCL all-reduce does -- the final mask."""
+    from ripcurrents_b200 import Context, sharded, synth
+    w, h, n = 224, 160, 9
+    fr = np.stack(synth.clip(w, h, n, seed=51))
+    P = (0.5, 2, 3, 2, 15, 1.2, 0)
+    seq = Context(0); seq.flow_configure_batch(w, h, *P, 8); seq.hist_reset()
+    masks = np.zeros((n, h, w), np.uint8)
+    _, res = seq.process_frames(fr[:1], 27, masks[:1]); _, res = seq.process_frames(fr[1:], 28, masks[1:])
+    ups = [r.UPPER for r in res]
+    acc_ref = seq.accumulator_get(w, h); hist_ref = seq.hist_get()[2]
+    blocks = [sharded.block_range(n - 1, 2, r) for r in range(2)]
+    backends = [sharded.GpuBackend(Context(0), w, h, P, 8) for _ in range(2)]
+    counts = [b.flows_and_counts(fr[lo:hi + 1]) for b, (lo, hi) in zip(backends, blocks)]
+    got_ups, acc = [], np.zeros(h * w, np.float32)
+    for r, (b, (lo, hi)) in enumerate(zip(backends, blocks)):
+        prefix = sharded.exclusive_prefix_counts(counts, r)
+        got_ups += b.aggregate(prefix, [28 + p for p in range(lo, hi)])
+        acc += b.accumulator()
+    assert got_ups == ups
+    assert np.array_equal(counts[0].sum(0) + counts[1].sum(0), hist_ref)
+    assert np.array_equal(acc.reshape(h, w), acc_ref)
+    # reporting-point mask from the combined accumulator == the sequential mask of the last frame
+    import ctypes as C
+    c = backends[1].ctx
+    p, _, _ = c.accumulator_device()
+    c.accumulator_reset(); c.synchronize()
+    # upload the all-reduced accumulator (what NCCL leaves in place) and ask for the mask
+    from ripcurrents_b200 import capi
+    capi._memcpy_h2d(p, acc)
+    assert np.array_equal(c.accumulator_mask(28 + n - 2), masks[n - 1])
+    for b in backends:
+        b.ctx.close()
+    seq.close()

@@ -1,0 +1,98 @@
+"""world_size-2 gloo test (CPU) of the frame-pair sharding orchestration (ripcurrents_b200/sharded.py): per-frame
+thresholds, total counts and the all-reduced accumulator must equal the sequential reference order
+(ripcurrents.cpp:319-439) -- with the CPU oracle standing in for the GPU engine."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleBackend:
+    def __init__(self, O, params, w, h):
+        self.O, self.P, self.w, self.h = O, params, w, h
+        self.acc = np.zeros(w * h, np.float32)
+        self.flows = []
+
+    def flows_and_counts(self, frames):
+        self.flows = [self.O.farneback(frames[i], frames[i + 1], *self.P) for i in range(len(frames) - 1)]
+        out = np.zeros((len(self.flows), 37, 50), np.int64)
+        for i, f in enumerate(self.flows):
+            st = self.O.HistState(); self.O.histogram(f, st); out[i] = st.hist2d
+        return out
+
+    def aggregate(self, prefix, framecounts):
+        st = self.O.HistState()
+        st.hist2d += prefix; st.hist += prefix.sum(0); st.histsum[0] = prefix.sum(); st.histsum2d += prefix.sum(1)
+        ups = []
+        for f, fc in zip(self.flows, framecounts):
+            self.O.histogram(f, st)
+            up, _, _ = self.O.thresholds(st)
+            self.O.classify_accumulate(f, up, fc, self.acc)
+            ups.append(up)
+        return ups
+
+    def accumulator(self):
+        return self.acc
+
+    def set_accumulator(self, a):
+        self.acc = a
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import oracle as O
+    from ripcurrents_b200 import sharded, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w, h, n = 96, 64, 8
+    fr = np.stack(synth.clip(w, h, n, seed=3))
+    P = (0.5, 1, 3, 2, 5, 1.1, 0)
+    lo, hi = sharded.block_range(n - 1, world, rank)
+    res = sharded.run_block(OracleBackend(O, P, w, h), fr, lo, hi, lambda p: 28 + p, dist=dist)
+    q.put((rank, lo, hi, res["upper"], res["counts_total"], res["accumulator"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_block_range():
+    from ripcurrents_b200 import sharded
+    assert [sharded.block_range(7, 2, r) for r in range(2)] == [(0, 4), (4, 7)]
+    assert [sharded.block_range(5, 8, r) for r in range(8)] == [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 5), (5, 5), (5, 5)]
+    got = [sharded.block_range(300, 8, r) for r in range(8)]
+    assert got[0][0] == 0 and got[-1][1] == 300 and all(a[1] == b[0] for a, b in zip(got, got[1:]))
+
+
+def test_two_rank_sharding_matches_sequential(oracle):
+    from ripcurrents_b200 import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(2)])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # sequential reference
+    w, h, n = 96, 64, 8
+    fr = np.stack(synth.clip(w, h, n, seed=3))
+    P = (0.5, 1, 3, 2, 5, 1.1, 0)
+    st = oracle.HistState(); acc = np.zeros(w * h, np.float32); ups = []
+    for i in range(n - 1):
+        f = oracle.farneback(fr[i], fr[i + 1], *P)
+        oracle.histogram(f, st)
+        up, _, _ = oracle.thresholds(st)
+        oracle.classify_accumulate(f, up, 28 + i, acc)
+        ups.append(up)
+    assert got[0][1:3] == (0, 4) and got[1][1:3] == (4, 7)
+    assert got[0][3] + got[1][3] == ups
+    for g in got:
+        assert np.array_equal(g[4], st.hist2d)
+        assert np.array_equal(g[5], acc)
+    assert acc.sum() > 0
