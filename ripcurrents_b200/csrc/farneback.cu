@@ -582,6 +582,72 @@ __global__ void update_flow_strict_kernel(FlowArgs a, int mi)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// FAST path, general window (winsize 4..33, box or Gaussian): one updateFlow iteration per launch.
+// CTA = 64x16 output pixels.  The five channels of M go through shared memory ONE AT A TIME (tile + halo staged with
+// replicate clamping, separable blur: vertical pass -> shared, horizontal pass -> registers), so a CTA needs only
+// (16+2m)(64+2m)+16(64+2m) floats of shared memory and the five blurred sums of each pixel stay in registers for
+// the fp32 solve; then either the fused updateMatrices (-> M of the next iteration) or the flow store.
+// ---------------------------------------------------------------------------------------------------
+template <bool FUSE>
+__global__ void __launch_bounds__(256)
+flow_iter_tiled_kernel(FlowArgs a, int mi)
+{
+    constexpr int TX = 64, TY = 16;
+    extern __shared__ float fsm[];
+    const int m = a.win.m, WP = TX + 2 * m, HP = TY + 2 * m;
+    float* sIn = fsm;                   // [HP][WP]
+    float* sV = fsm + HP * WP;          // [TY][WP]
+    const int w = a.w, h = a.h, j = blockIdx.z, tid = threadIdx.x;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const float* Min = a.M + (size_t)j * a.m_stride + (size_t)mi * 5 * a.plane;
+    const int lane = tid & 31, wrp = tid >> 5;
+    const int tx = tid & 63, tyb = tid >> 6;          // this thread's pixels: (tx, tyb + 4*i), i = 0..3
+    float s[4][5];
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        const float* P = Min + (size_t)c * a.plane;
+        for (int ry = wrp; ry < HP; ry += 8) {
+            const float* grow = P + (size_t)clampi(y0 - m + ry, 0, h - 1) * a.pitch;
+            for (int rx = lane; rx < WP; rx += 32) sIn[ry * WP + rx] = __ldg(grow + clampi(x0 - m + rx, 0, w - 1));
+        }
+        __syncthreads();
+        for (int idx = tid; idx < TY * WP; idx += 256) {
+            const int ty = idx / WP, cx = idx - ty * WP;
+            const float* col = sIn + (ty + m) * WP + cx;
+            float v = col[0] * a.win.k[0];
+            for (int i = 1; i <= m; i++) v = fmaf(col[i * WP] + col[-i * WP], a.win.k[i], v);
+            sV[idx] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float* row = sV + (tyb + 4 * i) * WP + tx + m;
+            float v = row[0] * a.win.k[0];
+            for (int k = 1; k <= m; k++) v = fmaf(row[k] + row[-k], a.win.k[k], v);
+            s[i][c] = v * a.win.post_scale;
+        }
+        __syncthreads();
+    }
+    const RView R0 = rview(a.R0(j), a.plane), R1 = rview(a.R1(j), a.plane);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int x = x0 + tx, y = y0 + tyb + 4 * i;
+        if (x >= w || y >= h) continue;
+        const float2 f = solve_fast(s[i][0], s[i][1], s[i][2], s[i][3], s[i][4]);
+        if (FUSE) {
+            float mm[5];
+            update_matrices_core<false>(x, y, f.x, f.y, w, h, R0, R1, a.pitch, mm);
+            float* Mo = a.M + (size_t)j * a.m_stride + (size_t)(mi ^ 1) * 5 * a.plane;
+            const size_t o = (size_t)y * a.pitch + x;
+#pragma unroll
+            for (int c = 0; c < 5; c++) Mo[c * a.plane + o] = mm[c];
+        } else {
+            reinterpret_cast<float2*>(a.out(j))[(size_t)y * w + x] = f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // FAST path, 3x3 window (winsize 2 or 3): ONE kernel per pyramid layer.  A 32x32 output tile carries a halo of
 // NT pixels; the structure matrices M never leave shared memory:
 //   stage 0      M0 = updateMatrices(initial flow) on (32+2NT)^2 cells (out-of-image cells = clamped pixel: replicate)
@@ -911,19 +977,34 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
             continue;
         }
         dim3 b(32, 8), g((L.w + 31) / 32, (L.h + 7) / 8, nb);
+        const bool tiled = !c->strict && c->win.m >= 1 && c->win.m <= 16;
         {
             KScope ks(c, K_UPDATE_MATRICES, (a.coarse ? 62.0 : 60.0) * npx);
-            update_matrices_kernel<true><<<g, b, 0, c->stream>>>(a, 0);
+            if (c->strict) update_matrices_kernel<true><<<g, b, 0, c->stream>>>(a, 0);
+            else update_matrices_kernel<false><<<g, b, 0, c->stream>>>(a, 0);
         }
+        const int m = c->win.m;
+        const size_t tsm = sizeof(float) * ((size_t)(16 + 2 * m) * (64 + 2 * m) + 16 * (size_t)(64 + 2 * m));
+        if (tiled && tsm > 48 * 1024) {
+            static size_t configured = 0;
+            if (tsm > configured) {
+                cudaFuncSetAttribute(flow_iter_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+                cudaFuncSetAttribute(flow_iter_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+                configured = tsm;
+            }
+        }
+        dim3 gt((L.w + 63) / 64, (L.h + 15) / 16, nb);
         int mi = 0;
         for (int it = 0; it < T; it++) {
             if (it < T - 1) {
                 KScope ks(c, K_FLOW_ITER_FUSED, 80.0 * npx);
-                update_flow_strict_kernel<true><<<g, b, 0, c->stream>>>(a, mi);
+                if (tiled) flow_iter_tiled_kernel<true><<<gt, 256, tsm, c->stream>>>(a, mi);
+                else update_flow_strict_kernel<true><<<g, b, 0, c->stream>>>(a, mi);
                 mi ^= 1;
             } else {
                 KScope ks(c, K_FLOW_ITER_FINAL, 28.0 * npx);
-                update_flow_strict_kernel<false><<<g, b, 0, c->stream>>>(a, mi);
+                if (tiled) flow_iter_tiled_kernel<false><<<gt, 256, tsm, c->stream>>>(a, mi);
+                else update_flow_strict_kernel<false><<<g, b, 0, c->stream>>>(a, mi);
             }
         }
         if (k == 0 && hist_delta) {
