@@ -16,6 +16,7 @@
 // (CV_32FC2, the output format).  Every array has a leading batch dimension: one
 // launch processes all frame pairs of a batch (blockIdx.z), which is what fills 148 SMs on the small pyramid layers.
 #include <string.h>
+#include <stdlib.h>
 #include "rc_internal.h"
 
 namespace {
@@ -63,13 +64,15 @@ pyr_tile_kernel(PyrArgs a, SmoothCoef sc)
 {
     extern __shared__ __align__(16) unsigned char psm[];
     const int TXD = a.TXD, TYD = a.TYD, SRW = a.SRW, SRH = a.SRH;
+    const int SRHP = SRH | 1;                                          // odd pitch of the transposed H-blur buffer
     const int lx = 31 - __clz(TXD);                                    // TXD is a power of two
-    float2* sT = reinterpret_cast<float2*>(psm);                       // [SRH][TXD] horizontally blurred pairs
-    float* sS = reinterpret_cast<float*>(sT + (size_t)SRH * TXD);      // [SRH][SRW] source region as fp32
+    float2* sT = reinterpret_cast<float2*>(psm);                       // [TXD][SRHP] horizontally blurred pairs
+    float* sS = reinterpret_cast<float*>(sT + (size_t)TXD * SRHP);     // [SRH][SRW] source region as fp32
     int* cS = reinterpret_cast<int*>(sS + (size_t)SRH * SRW);          // [TXD] sx, [TYD] sy
     float* cF = reinterpret_cast<float*>(cS + TXD + TYD);              // [TXD] fx, [TYD] fy
     int* gX = reinterpret_cast<int*>(cF + TXD + TYD);                  // [SRW] reflected source column of region col
-    const int tid = threadIdx.x, r = sc.ksize / 2;
+    const int tid = threadIdx.x, r = sc.ksize / 2, ks = sc.ksize;
+    const int lane = tid & 31, wrp = tid >> 5;
     const int X0 = blockIdx.x * TXD, Y0 = blockIdx.y * TYD;
     const uint8_t* img = a.img + (size_t)blockIdx.z * a.fstride;
     float* out = a.out + (size_t)blockIdx.z * a.ostride;
@@ -89,8 +92,29 @@ pyr_tile_kernel(PyrArgs a, SmoothCoef sc)
     const int ox = cS[0] - r, oy = cS[TXD] - r;
     for (int i = tid; i < SRW; i += 256) gX[i] = reflect101(ox + i, a.W);
     __syncthreads();
-    {   // stage the source region: warp = row, lane = column
-        const int lane = tid & 31, wrp = tid >> 5;
+    // stage the source region: warp = row.  Interior tiles of 4-byte aligned images read whole 32-bit words
+    // (coalesced, 4 pixels per load, several rows in flight); border / unaligned tiles gather bytes through the
+    // reflected column table.
+    const bool interior = ox >= 0 && ox + SRW <= a.W && oy >= 0 && oy + SRH <= a.H && (a.step & 3) == 0 &&
+                          (reinterpret_cast<size_t>(img) & 3) == 0;
+    if (interior) {
+        const int a0 = ox & ~3, sh = ox & 3;
+        const int nwords = (SRW + sh + 3) >> 2;
+#pragma unroll 4
+        for (int ry = wrp; ry < SRH; ry += 8) {
+            const unsigned int* grow = reinterpret_cast<const unsigned int*>(img + (size_t)(oy + ry) * a.step + a0);
+            float* srow = sS + ry * SRW - sh;
+            for (int j = lane; j < nwords; j += 32) {
+                const unsigned int v = __ldg(grow + j);
+                const int c = 4 * j;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int col = c + b - sh;
+                    if (col >= 0 && col < SRW) srow[c + b] = (float)((v >> (8 * b)) & 0xffu);
+                }
+            }
+        }
+    } else {
         for (int ry = wrp; ry < SRH; ry += 8) {
             const uint8_t* grow = img + (size_t)reflect101(oy + ry, a.H) * a.step;
             float* srow = sS + ry * SRW;
@@ -98,50 +122,68 @@ pyr_tile_kernel(PyrArgs a, SmoothCoef sc)
         }
     }
     __syncthreads();
-    // horizontal blur at the sampled columns, every staged row
-    for (int idx = tid; idx < (SRH << lx); idx += 256) {
-        const int ry = idx >> lx, tx = idx & (TXD - 1);
+    // horizontal blur at the two sampled columns of every destination column, every staged row.
+    // warp = destination column, lane = staged row: the odd row pitch makes the strided reads conflict-free, and the
+    // two sampled columns (adjacent except at the right border) share their taps.
+    for (int tx = wrp; tx < TXD; tx += 8) {
         const int sx = cS[tx];
-        const float* row = sS + ry * SRW + (sx - r - ox);
-        float s0 = __fmul_rn(sc.k[0], row[0]), s1 = 0.f;
-        if (a.two) {
-            const int d1 = (sx + 1 < a.W ? sx + 1 : a.W - 1) - sx;
-            s1 = __fmul_rn(sc.k[0], row[d1]);
-            for (int i = 1; i < sc.ksize; i++) {
-                s0 = __fadd_rn(s0, __fmul_rn(sc.k[i], row[i]));
-                s1 = __fadd_rn(s1, __fmul_rn(sc.k[i], row[i + d1]));
+        const int d1 = a.two ? (sx + 1 < a.W ? sx + 1 : a.W - 1) - sx : 0;
+        const int c0 = sx - r - ox;
+        for (int ry = lane; ry < SRH; ry += 32) {
+            const float* row = sS + ry * SRW + c0;
+            float prev = row[0];
+            float s0 = __fmul_rn(sc.k[0], prev), s1 = 0.f;
+            if (d1 == 1) {
+                for (int i = 1; i < ks; i++) {
+                    const float cur = row[i];
+                    s0 = __fadd_rn(s0, __fmul_rn(sc.k[i], cur));
+                    s1 = i == 1 ? __fmul_rn(sc.k[0], cur) : __fadd_rn(s1, __fmul_rn(sc.k[i - 1], cur));
+                }
+                s1 = __fadd_rn(s1, __fmul_rn(sc.k[ks - 1], row[ks]));
+            } else {
+                for (int i = 1; i < ks; i++) s0 = __fadd_rn(s0, __fmul_rn(sc.k[i], row[i]));
+                s1 = s0;        // identity resize, or the clamped last column (d1 == 0): both samples coincide
             }
-        } else {
-            for (int i = 1; i < sc.ksize; i++) s0 = __fadd_rn(s0, __fmul_rn(sc.k[i], row[i]));
+            sT[tx * SRHP + ry] = make_float2(s0, s1);
         }
-        sT[idx] = make_float2(s0, s1);
     }
     __syncthreads();
-    // vertical blur at the sampled rows + bilinear combination
+    // vertical blur at the two sampled rows + bilinear combination
     for (int idx = tid; idx < (TYD << lx); idx += 256) {
         const int ty = idx >> lx, tx = idx & (TXD - 1);
         const int X = X0 + tx, Y = Y0 + ty;
         if (X >= a.dw || Y >= a.dh) continue;
         const int sy = cS[TXD + ty];
-        const float2* colp = sT + ((sy - r - oy) << lx) + tx;
+        const float2* colp = sT + tx * SRHP + (sy - r - oy);
         float v;
         if (a.two) {
-            const int d1 = ((sy + 1 < a.H ? sy + 1 : a.H - 1) - sy) << lx;
+            const int d1 = (sy + 1 < a.H ? sy + 1 : a.H - 1) - sy;
             const float fx = cF[tx], fy = cF[TXD + ty];
-            const float2 p0 = colp[0], q0 = colp[d1];
-            float b00 = __fmul_rn(sc.k[0], p0.x), b01 = __fmul_rn(sc.k[0], p0.y);
-            float b10 = __fmul_rn(sc.k[0], q0.x), b11 = __fmul_rn(sc.k[0], q0.y);
-            for (int jj = 1; jj < sc.ksize; jj++) {
-                const float2 p = colp[jj << lx], q = colp[(jj << lx) + d1];
-                b00 = __fadd_rn(b00, __fmul_rn(sc.k[jj], p.x)); b01 = __fadd_rn(b01, __fmul_rn(sc.k[jj], p.y));
-                b10 = __fadd_rn(b10, __fmul_rn(sc.k[jj], q.x)); b11 = __fadd_rn(b11, __fmul_rn(sc.k[jj], q.y));
+            float2 p = colp[0];
+            float b00 = __fmul_rn(sc.k[0], p.x), b01 = __fmul_rn(sc.k[0], p.y), b10, b11;
+            if (d1 == 1) {
+                b10 = 0.f; b11 = 0.f;
+                for (int jj = 1; jj < ks; jj++) {
+                    p = colp[jj];
+                    b00 = __fadd_rn(b00, __fmul_rn(sc.k[jj], p.x)); b01 = __fadd_rn(b01, __fmul_rn(sc.k[jj], p.y));
+                    if (jj == 1) { b10 = __fmul_rn(sc.k[0], p.x); b11 = __fmul_rn(sc.k[0], p.y); }
+                    else { b10 = __fadd_rn(b10, __fmul_rn(sc.k[jj - 1], p.x)); b11 = __fadd_rn(b11, __fmul_rn(sc.k[jj - 1], p.y)); }
+                }
+                p = colp[ks];
+                b10 = __fadd_rn(b10, __fmul_rn(sc.k[ks - 1], p.x)); b11 = __fadd_rn(b11, __fmul_rn(sc.k[ks - 1], p.y));
+            } else {
+                for (int jj = 1; jj < ks; jj++) {
+                    p = colp[jj];
+                    b00 = __fadd_rn(b00, __fmul_rn(sc.k[jj], p.x)); b01 = __fadd_rn(b01, __fmul_rn(sc.k[jj], p.y));
+                }
+                b10 = b00; b11 = b01;
             }
             const float top = __fadd_rn(__fmul_rn(b00, 1.f - fx), __fmul_rn(b01, fx));
             const float bot = __fadd_rn(__fmul_rn(b10, 1.f - fx), __fmul_rn(b11, fx));
             v = __fadd_rn(__fmul_rn(top, 1.f - fy), __fmul_rn(bot, fy));
         } else {
             float s = __fmul_rn(sc.k[0], colp[0].x);
-            for (int jj = 1; jj < sc.ksize; jj++) s = __fadd_rn(s, __fmul_rn(sc.k[jj], colp[jj << lx].x));
+            for (int jj = 1; jj < ks; jj++) s = __fadd_rn(s, __fmul_rn(sc.k[jj], colp[jj].x));
             v = s;
         }
         out[(size_t)Y * a.pitch + X] = v;
@@ -427,6 +469,68 @@ __device__ __forceinline__ void update_matrices_core(int x, int y, float dx, flo
     m[2] = fadd<S>(fmul<S>(r5, r5), fmul<S>(r6, r6));
     m[3] = fadd<S>(fmul<S>(r4, r2), fmul<S>(r6, r3));
     m[4] = fadd<S>(fmul<S>(r6, r2), fmul<S>(r5, r3));
+}
+
+// Fast-path split of updateMatrices into a load half and a math half: the strip kernel issues the gathers of the
+// next row before it consumes the current one.
+struct UMIn {
+    float4 r0, t00, t01, t10, t11;
+    float r0_4, u00, u01, u10, u11;
+    float fx, fy, dx, dy;
+    bool inside;
+};
+
+__device__ __forceinline__ void um_load(UMIn& u, int x, int y, float dx, float dy, int w, int h, const RView& R0,
+                                        const RView& R1, int pitch)
+{
+    const int p = y * pitch + x;
+    const float fx = (float)x + dx, fy = (float)y + dy;
+    const float flx = floorf(fx), fly = floorf(fy);
+    const int x1 = (int)flx, y1 = (int)fly;
+    u.fx = fx - flx; u.fy = fy - fly; u.dx = dx; u.dy = dy;
+    u.r0 = __ldg(R0.A + p);
+    u.r0_4 = __ldg(R0.B + p);
+    u.inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+    // out-of-range gathers are redirected to a valid address near the pixel itself; their values are not used
+    const int q = u.inside ? y1 * pitch + x1 : (y < h - 1 ? p : p - pitch) - (x < w - 1 ? 0 : 1);
+    u.t00 = __ldg(R1.A + q); u.t01 = __ldg(R1.A + q + 1);
+    u.t10 = __ldg(R1.A + q + pitch); u.t11 = __ldg(R1.A + q + pitch + 1);
+    u.u00 = __ldg(R1.B + q); u.u01 = __ldg(R1.B + q + 1);
+    u.u10 = __ldg(R1.B + q + pitch); u.u11 = __ldg(R1.B + q + pitch + 1);
+}
+
+__device__ __forceinline__ void um_finish(const UMIn& u, int x, int y, int w, int h, float m[5])
+{
+    float r2, r3, r4, r5, r6;
+    if (u.inside) {
+        const float gx = 1.f - u.fx, gy = 1.f - u.fy;
+        const float a00 = gx * gy, a01 = u.fx * gy, a10 = gx * u.fy, a11 = u.fx * u.fy;
+#define RC_BILERP(c00, c01, c10, c11) (((a00 * (c00) + a01 * (c01)) + a10 * (c10)) + a11 * (c11))
+        r2 = RC_BILERP(u.t00.x, u.t01.x, u.t10.x, u.t11.x);
+        r3 = RC_BILERP(u.t00.y, u.t01.y, u.t10.y, u.t11.y);
+        r4 = (u.r0.z + RC_BILERP(u.t00.z, u.t01.z, u.t10.z, u.t11.z)) * 0.5f;
+        r5 = (u.r0.w + RC_BILERP(u.t00.w, u.t01.w, u.t10.w, u.t11.w)) * 0.5f;
+        r6 = (u.r0_4 + RC_BILERP(u.u00, u.u01, u.u10, u.u11)) * 0.25f;
+#undef RC_BILERP
+    } else {
+        r2 = r3 = 0.f;
+        r4 = u.r0.z; r5 = u.r0.w; r6 = u.r0_4 * 0.5f;
+    }
+    r2 = (u.r0.x - r2) * 0.5f;
+    r3 = (u.r0.y - r3) * 0.5f;
+    r2 = r2 + (r4 * u.dy + r6 * u.dx);
+    r3 = r3 + (r6 * u.dy + r5 * u.dx);
+    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+        auto bw = [](int d) { return d >= 5 ? 1.f : (d < 2 ? 0.14f : 0.4472f); };
+        float scale = __fmul_rn(__fmul_rn(__fmul_rn(bw(x), bw(w - x - 1)), bw(y)), bw(h - y - 1));
+        r2 = __fmul_rn(r2, scale); r3 = __fmul_rn(r3, scale); r4 = __fmul_rn(r4, scale);
+        r5 = __fmul_rn(r5, scale); r6 = __fmul_rn(r6, scale);
+    }
+    m[0] = r4 * r4 + r6 * r6;
+    m[1] = (r4 + r5) * r6;
+    m[2] = r5 * r5 + r6 * r6;
+    m[3] = r4 * r2 + r6 * r3;
+    m[4] = r6 * r2 + r5 * r3;
 }
 
 // Flow initialisation of Appendix A.4 at pixel (x, y) of a w x h layer from the coarser layer's flow.
@@ -797,6 +901,142 @@ flow_layer_kernel(FlowArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// FAST path, 3x3 window, register/shuffle formulation of the same fused layer: a WARP owns a 32-column strip
+// (32 - 2*NT useful columns) and marches down a segment of rows.  Lane = column.  The last two rows of M of every
+// iteration level live in registers; the vertical 3-sum is formed from them, the horizontal one with two shuffles
+// per channel -- no shared memory for M, no block barriers, every warp independent.  Replicate borders: level-0 rows
+// are evaluated at clamped pixels, deeper levels duplicate their first/last real row and copy the flow of the
+// clamped column before updateMatrices, which reproduces M at the clamped pixel exactly.
+// ---------------------------------------------------------------------------------------------------
+template <int NT, bool BOX>
+__global__ void __launch_bounds__(256)
+flow_strip_kernel(FlowArgs a, int SEG)
+{
+    constexpr int UW = 32 - 2 * NT;
+    __shared__ unsigned int sH[RC_HIST_CELLS];
+    __shared__ unsigned short sKeys[256];
+    __shared__ int sNKeys;
+    const int w = a.w, h = a.h, j = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, pitch = a.pitch;
+    const bool do_hist = a.hist_delta != nullptr;
+    if (do_hist) {
+        for (int i = tid; i < RC_HIST_CELLS; i += 256) sH[i] = 0;
+        if (tid == 0) sNKeys = 0;
+        __syncthreads();
+    }
+    const int sx0 = (blockIdx.x * 8 + wrp) * UW;
+    const int y0 = blockIdx.y * SEG;
+    if (sx0 < w) {
+        const int xv = sx0 - NT + lane;
+        const int x = clampi(xv, 0, w - 1);
+        const bool col_out = lane >= NT && lane < 32 - NT && xv < w;
+        const bool need_fix = (sx0 - NT < 0) || (sx0 - NT + 31 >= w);
+        const int src_lane = x - (sx0 - NT);                 // lane that owns the clamped column
+        const RView R0 = rview(a.R0(j), a.plane), R1 = rview(a.R1(j), a.plane);
+        const float2* coarse = a.coarse ? reinterpret_cast<const float2*>(a.coarse + (size_t)j * a.coarse_stride) : nullptr;
+        int csx = 0; float cfx = 0.f;
+        if (coarse) resize_coef(x, a.cw, a.sxs, csx, cfx);
+        const float k0 = a.win.k[0], k1 = a.win.k[1], ps = a.win.post_scale;
+        float2* outp = reinterpret_cast<float2*>(a.out(j));
+
+        float A[NT][5], B[NT][5];
+        int nfed[NT];
+#pragma unroll
+        for (int it = 0; it < NT; it++) nfed[it] = 0;
+        const int vbeg = max(y0 - NT, 0);
+        const int vend = min(y0 + SEG - 1 + NT, h + NT - 1);
+        // level-0 gathers run one row ahead of the row being consumed
+        UMIn pre;
+        auto prefetch0 = [&](int r) {
+            float2 fi = make_float2(0.f, 0.f);
+            if (coarse) {
+                int csy; float cfy;
+                resize_coef(r, a.ch, a.sys, csy, cfy);
+                fi = upsample_flow_tab(coarse, a.cw, a.ch, csx, cfx, csy, cfy, a.fscale);
+            }
+            um_load(pre, x, r, fi.x, fi.y, w, h, R0, R1, pitch);
+        };
+        prefetch0(min(vbeg, h - 1));
+#pragma unroll 1
+        for (int v = vbeg; v <= vend; v++) {
+            bool produced = false;
+            float2 f = make_float2(0.f, 0.f);
+            float C0[5];
+            if (v < h) um_finish(pre, x, v, w, h, C0);
+            if (v + 1 < h && v + 1 <= vend) prefetch0(v + 1);
+#pragma unroll
+            for (int it = 0; it < NT; it++) {
+                const int r = v - it;
+                float C[5];
+                bool have = false;
+                if (r >= 0 && r < h) {
+                    if (it == 0) {
+#pragma unroll
+                        for (int c = 0; c < 5; c++) C[c] = C0[c];
+                        have = true;
+                    } else if (produced) {
+                        if (need_fix) { f.x = __shfl_sync(0xffffffffu, f.x, src_lane); f.y = __shfl_sync(0xffffffffu, f.y, src_lane); }
+                        update_matrices_core<false>(x, r, f.x, f.y, w, h, R0, R1, pitch, C);
+                        have = true;
+                    }
+                } else if (r == h && nfed[it] > 0) {
+#pragma unroll
+                    for (int c = 0; c < 5; c++) C[c] = B[it][c];
+                    have = true;
+                }
+                produced = false;
+                if (!have) continue;
+                if (nfed[it] == 0) {
+#pragma unroll
+                    for (int c = 0; c < 5; c++) { B[it][c] = C[c]; A[it][c] = C[c]; }
+                    nfed[it] = (r == 0) ? 2 : 1;
+                    continue;
+                }
+                if (nfed[it] >= 2) {
+                    float sv[5];
+#pragma unroll
+                    for (int c = 0; c < 5; c++) {
+                        const float vs = BOX ? B[it][c] + (A[it][c] + C[c]) : fmaf(A[it][c] + C[c], k1, B[it][c] * k0);
+                        const float lft = __shfl_up_sync(0xffffffffu, vs, 1), rgt = __shfl_down_sync(0xffffffffu, vs, 1);
+                        sv[c] = (BOX ? vs + (lft + rgt) : fmaf(lft + rgt, k1, vs * k0)) * ps;
+                    }
+                    f = solve_fast(sv[0], sv[1], sv[2], sv[3], sv[4]);
+                    produced = true;
+                }
+#pragma unroll
+                for (int c = 0; c < 5; c++) { A[it][c] = B[it][c]; B[it][c] = C[c]; }
+                nfed[it]++;
+            }
+            const int yo = v - NT;
+            const bool row_out = produced && yo >= y0 && yo < y0 + SEG && yo < h;      // warp-uniform
+            if (row_out) {
+                if (col_out) outp[yo * w + xv] = f;
+                if (do_hist) {
+                    const int key = col_out ? hist_key_fast(f.x, f.y) : -1;
+                    const unsigned peers = __match_any_sync(0xffffffffu, key);
+                    if (key >= 0 && (int)(__ffs(peers) - 1) == lane) {
+                        if (atomicAdd(&sH[key], __popc(peers)) == 0) {
+                            const int slot = atomicAdd(&sNKeys, 1);
+                            if (slot < 256) sKeys[slot] = (unsigned short)key;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (do_hist) {
+        __syncthreads();
+        unsigned int* dst = a.hist_delta + (size_t)j * RC_HIST_CELLS;
+        const int nk = sNKeys;
+        if (nk <= 256) {
+            if (tid < nk) { const int k = sKeys[tid]; atomicAdd(&dst[k], sH[k]); }
+        } else {
+            for (int i = tid; i < RC_HIST_CELLS; i += 256)
+                if (sH[i]) atomicAdd(&dst[i], sH[i]);
+        }
+    }
+}
+
 // direction/speed key of one flow vector: bit-exact twin of aggregate.cu's hist_key (cv::cartToPolar restated,
 // SURVEY.md section 8(c)); intrinsics keep it independent of this file's FMA contraction.
 __device__ __forceinline__ int hist_key_fast(float x, float y)
@@ -907,7 +1147,7 @@ void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fs
             a.TXD = cand[i][0]; a.TYD = cand[i][1];
             a.SRW = (int)(a.sxs * (a.TXD - 1)) + 2 * r + 4; a.SRH = (int)(a.sys * (a.TYD - 1)) + 2 * r + 4;
             a.SRW |= 1;       // odd row pitch: column-strided reads of the staged region spread over the banks
-            smem = sizeof(float2) * (size_t)a.SRH * a.TXD + 4 * (size_t)a.SRH * a.SRW + 8 * (size_t)(a.TXD + a.TYD) +
+            smem = sizeof(float2) * (size_t)(a.SRH | 1) * a.TXD + 4 * (size_t)a.SRH * a.SRW + 8 * (size_t)(a.TXD + a.TYD) +
                    4 * (size_t)a.SRW;
             if (smem <= 100 * 1024) break;
         }
@@ -965,6 +1205,22 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         if (fused_ok) {
             dim3 g((L.w + 31) / 32, (L.h + 31) / 32, nb);
             KScope ks(c, K_FLOW_LAYER, (a.coarse ? 50.0 : 48.0) * npx);
+            static const int use_strip = getenv("RC_FLOW_STRIP") ? 1 : 0;     // A/B switch: register/shuffle strip kernel
+            if (use_strip) {
+                const int SEG = L.h >= 512 ? 64 : 32;
+                const int UW = 32 - 2 * T;
+                dim3 gs(((L.w + UW - 1) / UW + 7) / 8, (L.h + SEG - 1) / SEG, nb);
+                if (!c->win.gaussian) {
+                    if (T == 1) flow_strip_kernel<1, true><<<gs, 256, 0, c->stream>>>(a, SEG);
+                    else if (T == 2) flow_strip_kernel<2, true><<<gs, 256, 0, c->stream>>>(a, SEG);
+                    else flow_strip_kernel<3, true><<<gs, 256, 0, c->stream>>>(a, SEG);
+                } else {
+                    if (T == 1) flow_strip_kernel<1, false><<<gs, 256, 0, c->stream>>>(a, SEG);
+                    else if (T == 2) flow_strip_kernel<2, false><<<gs, 256, 0, c->stream>>>(a, SEG);
+                    else flow_strip_kernel<3, false><<<gs, 256, 0, c->stream>>>(a, SEG);
+                }
+                continue;
+            }
             if (!c->win.gaussian) {
                 if (T == 1) flow_layer_kernel<1, true><<<g, 256, 0, c->stream>>>(a);
                 else if (T == 2) flow_layer_kernel<2, true><<<g, 256, 0, c->stream>>>(a);
