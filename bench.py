@@ -47,7 +47,7 @@ UNIT = "pairs/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs per worker for the CPU legs (0 = auto)")
@@ -92,14 +92,19 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, cv2 is not None
 
 
-def cpu_leg(pairs_per_worker, workers):
+def cpu_leg(pairs_per_worker, workers, pool=None):
     """Throughput of the CPU path with `workers` independent processes (OpenCV's Farneback is single-threaded,
     so frame-pair parallelism is how a host uses its cores).  Returns (pairs/s, cores, kind, sample)."""
     import multiprocessing as mp
-    ctx = mp.get_context("spawn")
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(workers)
     t0 = time.perf_counter()
-    with ctx.Pool(workers) as pool:
+    try:
         res = pool.map(_cpu_worker, [(100 + i, pairs_per_worker, W, H) for i in range(workers)])
+    finally:
+        if own:
+            pool.close(); pool.join()
     wall = time.perf_counter() - t0
     busy = max(r[0] for r in res)
     have_cv2 = all(r[1] for r in res)
@@ -124,17 +129,20 @@ def _cv2_version():
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    import multiprocessing as mp
     workers = min(os.cpu_count() or 1, 32)
-    per = args.cpu_pairs or max(2, min(6, args.steps))
-    # W warm-up + K steps: each "step" of this arm is one bounded sample (per worker `per` pairs)
+    per = args.cpu_pairs or 3
+    # W warm-up + K steps: each "step" of this arm is one bounded sample (`per` pairs on each of `workers` processes);
+    # the whole run is capped at ~4 minutes
     vals = []
     t_all = time.perf_counter()
-    for s in range(args.warmup + args.steps):
-        v, cores, kind, sample = cpu_leg(per, workers)
-        if s >= args.warmup:
-            vals.append(v)
-        if time.perf_counter() - t_all > 240 and len(vals) >= 1:
-            break
+    with mp.get_context("spawn").Pool(workers) as pool:
+        for s in range(args.warmup + args.steps):
+            v, cores, kind, sample = cpu_leg(per, workers, pool)
+            if s >= args.warmup:
+                vals.append(v)
+            if time.perf_counter() - t_all > 200 and len(vals) >= 1:
+                break
     value = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * per * workers / value,
@@ -147,36 +155,56 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-class ClockSampler(threading.Thread):
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed regions (one persistent `-lms 20` process, parsed afterwards)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
     def __init__(self, index):
-        super().__init__(daemon=True)
         self.index = index
-        self.samples = []
-        self.stop_flag = False
+        self.proc = None
+        self.lines = []
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+            time.sleep(0.3)          # let the first samples arrive before the region starts
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
+                self.proc.wait(timeout=3)
             except Exception:
-                pass
-            time.sleep(0.1)
+                self.proc.kill()
 
-    def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+    def summary(self, t0=None, t1=None):
+        rows = []
+        for t, line in self.lines:
+            if t0 is not None and not (t0 <= t <= t1):
+                continue
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) >= 7:
+                rows.append(f)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(pw) if pw else None}
 
 
 class DevArr:
@@ -285,10 +313,11 @@ def run_ours(args, rank, world, local_rank):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_region0 = time.perf_counter()
     ms_dev, launches = timed(step_device, args.steps, max(args.warmup, 3))
     ms_e2e, _ = timed(step_e2e, args.steps, 2)
-    sampler.stop_flag = True
-    sampler.join(timeout=3)
+    t_region1 = time.perf_counter()
+    sampler.stop()
 
     pairs = FRAMES_PER_STEP * args.steps * world
     value = pairs / (ms_dev * 1e-3)
@@ -334,13 +363,13 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (+f64 accumulators)",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic moving texture (ripcurrents_b200/synth.py), %d-frame clip per stream" % CLIP_FRAMES,
                 "config": config_dict(world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": FRAMES_PER_STEP * W * H,
                         "d2h_bytes_per_step": FRAMES_PER_STEP * (W * H + 320), "ms_per_step": ms_e2e / args.steps,
                         "api": "rc_submit_frames(16 pinned host frames) -> 16 outmasks + threshold records on the host, rc_wait"},
-                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "kernels": kernels,
+                "gpu_launches": int(launches), "clocks": sampler.summary(t_region0, t_region1 + 0.05), "roofline": roofline, "kernels": kernels,
                 "check": {"last_UPPER": float(h_results[(state["step"] - 1) & 1][FRAMES_PER_STEP - 1].UPPER),
                           "histsum": int(h_results[(state["step"] - 1) & 1][FRAMES_PER_STEP - 1].histsum)}}
         if world == 1 and not args.no_cpu_baseline:

@@ -28,3 +28,22 @@ def load_golden(name):
     P = z["params"]
     params = (float(P[0]), int(P[1]), int(P[2]), int(P[3]), int(P[4]), float(P[5]), int(P[6]))
     return z["frames"], z["flows"], params
+
+
+def cv2_both(cv2, a, b, P):
+    """OpenCV's two code paths (setUseOptimized on / off).  They disagree with each other on a handful of
+    ill-conditioned pixels per frame, so the max-EPE gate uses the nearer of the two."""
+    cv2.setUseOptimized(True)
+    r1 = cv2.calcOpticalFlowFarneback(a, b, None, *P)
+    cv2.setUseOptimized(False)
+    r2 = cv2.calcOpticalFlowFarneback(a, b, None, *P)
+    cv2.setUseOptimized(True)
+    return r1, r2
+
+
+def epe_vs_cv2(mine, r1, r2):
+    """-> (mean EPE vs the default path, max over pixels of the distance to the nearer OpenCV answer,
+           fraction of pixels where OpenCV disagrees with itself by more than 1e-3 px)"""
+    d1 = np.sqrt(((mine - r1) ** 2).sum(-1)); d2 = np.sqrt(((mine - r2) ** 2).sum(-1))
+    self_d = np.sqrt(((r1 - r2) ** 2).sum(-1))
+    return float(d1.mean()), float(np.minimum(d1, d2).max()), float((self_d > 1e-3).mean())
