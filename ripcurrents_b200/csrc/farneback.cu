@@ -190,6 +190,51 @@ pyr_tile_kernel(PyrArgs a, SmoothCoef sc)
     }
 }
 
+// Exact 2:1 layer with a 3-tap presmooth (pyr_scale 0.5, layer 1): the bilinear resize samples source columns
+// 2X, 2X+1 with weight 1/2 each (same for rows), so a destination pixel is a fixed 4x4 source window.  Each thread
+// produces two adjacent destination pixels from four rows of (one aligned 4-byte load + two edge bytes); arithmetic
+// order identical to pyr_tile_kernel (taps in order, products and sums rounded separately).
+__global__ void __launch_bounds__(256)
+pyr_half_kernel(const uint8_t* __restrict__ img, size_t step, size_t fstride, int W, int H, int dw, int dh, float k0,
+                float k1, float k2, float* __restrict__ out, int pitch, size_t ostride)
+{
+    const int X = (blockIdx.x * 64 + (threadIdx.x & 63)) * 2;       // dw is even (W % 4 == 0)
+    const int Y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (X >= dw || Y >= dh) return;
+    img += (size_t)blockIdx.z * fstride;
+    out += (size_t)blockIdx.z * ostride;
+    const int x = 2 * X;                                            // source columns x-1 .. x+4
+    const int xl = x > 0 ? x - 1 : 1, xr = x + 4 < W ? x + 4 : W - 2;
+    float hb[4][4];                                                 // [source row 2Y-1+rr][source column x+i] after the H blur
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        int yy = 2 * Y - 1 + rr;
+        yy = yy < 0 ? 1 : (yy >= H ? H - 2 : yy);
+        const uint8_t* row = img + (size_t)yy * step;
+        const uchar4 m = *reinterpret_cast<const uchar4*>(row + x);
+        const float v[6] = {(float)row[xl], (float)m.x, (float)m.y, (float)m.z, (float)m.w, (float)row[xr]};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            hb[rr][i] = __fadd_rn(__fadd_rn(__fmul_rn(k0, v[i]), __fmul_rn(k1, v[i + 1])), __fmul_rn(k2, v[i + 2]));
+    }
+    float r[2];
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+        float b[2][2];                                              // [sampled row][sampled column]
+#pragma unroll
+        for (int sr = 0; sr < 2; sr++)
+#pragma unroll
+            for (int sc = 0; sc < 2; sc++) {
+                const int c = 2 * d + sc;
+                b[sr][sc] = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[sr][c]), __fmul_rn(k1, hb[sr + 1][c])), __fmul_rn(k2, hb[sr + 2][c]));
+            }
+        const float top = __fadd_rn(__fmul_rn(b[0][0], 0.5f), __fmul_rn(b[0][1], 0.5f));
+        const float bot = __fadd_rn(__fmul_rn(b[1][0], 0.5f), __fmul_rn(b[1][1], 0.5f));
+        r[d] = __fadd_rn(__fmul_rn(top, 0.5f), __fmul_rn(bot, 0.5f));
+    }
+    *reinterpret_cast<float2*>(out + (size_t)Y * pitch + X) = make_float2(r[0], r[1]);
+}
+
 // Layer 0 (no resize; OpenCV's 3-tap [1/4 1/2 1/4] presmooth): each thread produces 4 adjacent pixels from three
 // 4-byte row loads + two edge bytes per row.  Same tap order and separately rounded products as the tile kernel.
 __global__ void __launch_bounds__(256)
@@ -1135,9 +1180,22 @@ void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fs
         if (!a.two && L.smooth.ksize == 3 && W % 4 == 0 && W >= 8 && H >= 2 && step % 4 == 0 && fstride % 4 == 0 &&
             (reinterpret_cast<size_t>(d_frames) & 3) == 0) {
             dim3 g((W / 4 + 63) / 64, (H + 3) / 4, nb);
-            KScope ks(c, K_PYR_V, ((double)W * H + 4.0 * L.w * L.h) * nb);
-            pyr0_kernel<<<g, 256, 0, c->stream>>>(d_frames, step, fstride, W, H, L.smooth.k[0], L.smooth.k[1],
-                                                 L.smooth.k[2], L.I, L.pitch, (size_t)L.pitch * L.h);
+            {
+                KScope ks(c, K_PYR_V, ((double)W * H + 4.0 * L.w * L.h) * nb);
+                pyr0_kernel<<<g, 256, 0, c->stream>>>(d_frames, step, fstride, W, H, L.smooth.k[0], L.smooth.k[1],
+                                                     L.smooth.k[2], L.I, L.pitch, (size_t)L.pitch * L.h);
+            }
+            launch_polyexp(c, L, nb, first_slot);
+            continue;
+        }
+        if (a.two && L.smooth.ksize == 3 && W == 2 * L.w && H == 2 * L.h && W % 4 == 0 && W >= 8 && H >= 4 && step % 4 == 0 &&
+            fstride % 4 == 0 && (reinterpret_cast<size_t>(d_frames) & 3) == 0) {
+            dim3 g((L.w / 2 + 63) / 64, (L.h + 3) / 4, nb);
+            {
+                KScope ks(c, K_PYR_V, 4.0 * L.w * L.h * nb);
+                pyr_half_kernel<<<g, 256, 0, c->stream>>>(d_frames, step, fstride, W, H, L.w, L.h, L.smooth.k[0],
+                                                         L.smooth.k[1], L.smooth.k[2], L.I, L.pitch, (size_t)L.pitch * L.h);
+            }
             launch_polyexp(c, L, nb, first_slot);
             continue;
         }
