@@ -9,7 +9,7 @@
 
 #define RC_VERSION 101
 
-const char* const rc_kernel_names[K_COUNT] = {"pyr_unused", "pyramid", "polyexp", "update_matrices", "flow_iter_fused",
+const char* const rc_kernel_names[K_COUNT] = {"reserved", "pyramid", "polyexp", "update_matrices", "flow_iter_fused",
                                               "flow_iter_final", "flow_layer_fused", "polar_hist", "thresholds",
                                               "classify", "window_mean", "advect", "streakline", "misc"};
 
@@ -478,7 +478,6 @@ int rc_flow_configure_batch(rc_ctx* c, int w, int h, double pyr_scale, int level
         int ks = round_half_even(sigma * 5.0) | 1; if (ks < 3) ks = 3;
         if (ks > RC_MAX_SMOOTH_TAPS) { rc = fail(c, RC_ERR_UNSUPPORTED, "pyramid too deep (smoothing kernel > 255 taps)%s"); break; }
         make_smooth(L.smooth, sigma, ks);
-        L.htmp_stride = 2 * (size_t)L.w * h;
         const bool fused = !c->strict && winsize / 2 == 1 && iterations <= 3;
         if ((rc = dev_alloc(c, (void**)&L.I, sizeof(float) * L.plane * B)) ||
             (rc = dev_alloc(c, (void**)&L.R, sizeof(float) * 5 * L.plane * (B + 1))) ||

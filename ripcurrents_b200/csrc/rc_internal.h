@@ -17,7 +17,7 @@
 #define RC_HIST_CELLS (RC_HIST_ROWS * RC_HIST_BINS)
 
 // kernel classes for rc_profile_* (per-launch CUDA-event timing) -- order matches rc_kernel_names[]
-enum RcKernelId { K_PYR_H = 0, K_PYR_V, K_POLYEXP, K_UPDATE_MATRICES, K_FLOW_ITER_FUSED, K_FLOW_ITER_FINAL,
+enum RcKernelId { K_RESERVED = 0, K_PYR_V, K_POLYEXP, K_UPDATE_MATRICES, K_FLOW_ITER_FUSED, K_FLOW_ITER_FINAL,
                   K_FLOW_LAYER, K_POLAR_HIST, K_THRESHOLDS, K_CLASSIFY, K_WINDOW, K_ADVECT, K_STREAKLINE, K_MISC,
                   K_COUNT };
 extern const char* const rc_kernel_names[K_COUNT];
@@ -58,8 +58,7 @@ struct FarnebackParams {
 
 // One pyramid layer.  All arrays carry a leading batch / ring dimension.
 //   I     [B]      presmoothed layer image of each new frame of the batch (row pitch `pitch`)
-//   htmp  [B]      pass-1 scratch of the pyramid kernel (H rows x 2*w floats)
-//   R     [B+1]    ring of polynomial expansions, 5 planes each (plane = pitch*h floats)
+//   R     [B+1]    ring of polynomial expansions, "4+1" layout: float4 plane + float plane (plane = pitch*h pixels)
 //   M     [B][2]   G/h matrices ping-pong, 5 planes each (only the unfused path uses them)
 //   flow  [B]      dense w*h*2 (layers k >= 1; layer 0 writes into the context's flow ring)
 struct Layer {
@@ -67,11 +66,9 @@ struct Layer {
     size_t plane = 0;
     SmoothCoef smooth;
     float* I = nullptr;
-    float* htmp = nullptr;
     float* R = nullptr;
     float* M = nullptr;
     float* flow = nullptr;
-    size_t htmp_stride = 0;      // floats per batch element
     __host__ __device__ float* Rslot(int s) const { return R + (size_t)s * 5 * plane; }
 };
 
