@@ -217,6 +217,20 @@ int rc_create_accumulationbuffer(rc_ctx* ctx, float* accumulator3, size_t acc_st
                                  size_t acc2_step, float* out3, size_t out_step, uint8_t* outmask, size_t mask_step, int w,
                                  int h, int framecount);
 
+/* ---- frame ingest ---------------------------------------------------------------
+ * cv::resize(frame, subframe, Size(dst_w,dst_h), 0, 0, INTER_LINEAR) + cv::cvtColor(subframe, gray, COLOR_BGR2GRAY):
+ * ripcurrents.cpp:209-210, main.cpp:258-259,1111-1112.  8-bit, OpenCV's fixed-point arithmetic, bit-exact against
+ * cv2 4.13.0.  flags: RC_INGEST_GRAY14 selects OpenCV 3.4's 14-bit gray weights (1868/9617/4899) instead of the
+ * 15-bit ones of OpenCV 4 (3735/19235/9798). */
+#define RC_INGEST_GRAY14 1
+int rc_ingest_bgr(rc_ctx* ctx, const uint8_t* bgr, size_t step, int src_w, int src_h, uint8_t* gray, size_t gray_step,
+                  int dst_w, int dst_h, int flags);
+/* rc_submit_frames fed with BGR camera frames of any size: H2D of the BGR frames, ingest on the device to the
+ * configured working size, then the same pipeline.  Same asynchronous contract as rc_submit_frames (rc_wait). */
+int rc_submit_frames_bgr(rc_ctx* ctx, const uint8_t* bgr_frames, size_t step, size_t frame_stride, int src_w, int src_h,
+                         int count, int framecount0, int ingest_flags, uint8_t* outmasks, size_t mask_stride,
+                         rc_frame_result* results);
+
 /* ---- fused per-frame step (what main()'s loop body does between video.read and imshow) ----------- */
 
 /* rc_flow_push + rc_polar_hist + rc_thresholds + rc_classify_accumulate (+ rc_window_update when a window is

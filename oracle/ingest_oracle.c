@@ -1,0 +1,58 @@
+/*
+ * oracle/ingest_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement of the frame ingest that precedes the flow call in every loop of the reference
+ * (SURVEY.md section 8(f), rank 1):
+ *     resize(frame, subframe, Size(XDIM,YDIM), 0, 0, INTER_LINEAR);   ripcurrents.cpp:209, main.cpp:258,1111
+ *     cvtColor(subframe, f1, COLOR_BGR2GRAY);                         ripcurrents.cpp:210, main.cpp:259,1112
+ * Both are OpenCV code (imgproc), absent from /root/reference; restated from OpenCV's published fixed-point scheme
+ * and pinned BIT-EXACTLY against cv2 4.13.0 (tests/golden/ingest.npz, tests/test_oracle_ingest.py):
+ *   resize 8U bilinear: coefficients round((1-f)*2048), round(f*2048); horizontal pass keeps 11 fractional bits;
+ *                       vertical pass ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2 >> 2
+ *   BGR2GRAY 8U:        (B*3735 + G*19235 + R*9798 + 2^14) >> 15     (OpenCV >= 4.x; 3.4 used 14-bit 1868/9617/4899)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+/* horizontal: index and weight are clamped together (sx<0 -> 0,f=0; sx>=sw-1 -> sw-1,f=0);
+ * vertical (clamp_f == 0): the weight is kept and the two ROW INDICES are clipped individually, as cv::resize does */
+static void coef(int d, int sn, int dn, int clamp_f, int* s0, int* a0, int* a1)
+{
+    double scale = (double)sn / (double)dn;
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (clamp_f) {
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+    }
+    *s0 = s;
+    *a0 = (int)nearbyintf((1.f - f) * 2048.f);
+    *a1 = (int)nearbyintf(f * 2048.f);
+}
+
+/* bgr: sh x sw x 3 u8 (row stride `step`); gray: dh x dw u8 (dense).  legacy14 != 0 selects OpenCV 3.4's gray weights. */
+void rc_oracle_ingest_bgr(const uint8_t* bgr, size_t step, int sw, int sh, uint8_t* gray, int dw, int dh, int legacy14)
+{
+    int x, y, c;
+    for (y = 0; y < dh; y++) {
+        int sy, b0, b1, sy1;
+        coef(y, sh, dh, 0, &sy, &b0, &b1);
+        sy1 = sy + 1 < 0 ? 0 : (sy + 1 < sh ? sy + 1 : sh - 1);
+        sy = sy < 0 ? 0 : (sy < sh ? sy : sh - 1);
+        for (x = 0; x < dw; x++) {
+            int sx, a0, a1, sx1, px[3];
+            coef(x, sw, dw, 1, &sx, &a0, &a1);
+            sx1 = sx + 1 < sw ? sx + 1 : sw - 1;
+            for (c = 0; c < 3; c++) {
+                int r0 = bgr[(size_t)sy * step + 3 * sx + c] * a0 + bgr[(size_t)sy * step + 3 * sx1 + c] * a1;
+                int r1 = bgr[(size_t)sy1 * step + 3 * sx + c] * a0 + bgr[(size_t)sy1 * step + 3 * sx1 + c] * a1;
+                px[c] = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+                if (px[c] > 255) px[c] = 255;
+            }
+            if (legacy14) gray[(size_t)y * dw + x] = (uint8_t)((px[0] * 1868 + px[1] * 9617 + px[2] * 4899 + (1 << 13)) >> 14);
+            else gray[(size_t)y * dw + x] = (uint8_t)((px[0] * 3735 + px[1] * 19235 + px[2] * 9798 + (1 << 14)) >> 15);
+        }
+    }
+}

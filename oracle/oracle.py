@@ -26,7 +26,7 @@ ADV_PATHLINE, ADV_LEGACY, ADV_MODULE, ADV_CUT5, ADV_FIXED100, ADV_FIELD, ADV_GET
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("farneback_oracle.c", "aggregate_oracle.c", "advect_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("farneback_oracle.c", "aggregate_oracle.c", "advect_oracle.c", "ingest_oracle.c")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs if os.path.exists(s))):
         return _SO
@@ -200,3 +200,13 @@ def streakline_step(flow, emitters, vertices, count, dt=1.0):
     assert vertices.dtype == np.float32 and count.dtype == np.int32 and emitters.dtype == np.float32
     lib().rc_oracle_streakline_step(_p(flow), C.c_int(w), C.c_int(h), _p(emitters), C.c_int(E), _p(vertices),
                                     _p(count), C.c_int(cap), C.c_float(dt))
+
+
+def ingest_bgr(bgr, dw, dh, legacy14=False):
+    """resize(INTER_LINEAR) + cvtColor(BGR2GRAY) of ripcurrents.cpp:209-210 (oracle/ingest_oracle.c)."""
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    sh, sw, _ = bgr.shape
+    out = np.empty((dh, dw), np.uint8)
+    lib().rc_oracle_ingest_bgr(_p(bgr), C.c_size_t(sw * 3), C.c_int(sw), C.c_int(sh), _p(out), C.c_int(dw), C.c_int(dh),
+                               C.c_int(1 if legacy14 else 0))
+    return out

@@ -23,7 +23,7 @@ SYMBOLS = [
     "rc_hist_reset", "rc_polar_hist", "rc_hist_get", "rc_hist_add", "rc_hist_device", "rc_cart_to_polar",
     "rc_thresholds", "rc_accumulator_reset", "rc_classify_accumulate", "rc_accumulator_get",
     "rc_accumulator_device", "rc_window_configure", "rc_window_update", "rc_window_get", "rc_window_device",
-    "rc_subtract_mean", "rc_batch_hist", "rc_aggregate_last", "rc_accumulator_mask", "rc_hist_from_polar", "rc_create_flow", "rc_create_accumulationbuffer", "rc_advect", "rc_streakline_step", "rc_process_frame",
+    "rc_subtract_mean", "rc_batch_hist", "rc_aggregate_last", "rc_accumulator_mask", "rc_ingest_bgr", "rc_submit_frames_bgr", "rc_hist_from_polar", "rc_create_flow", "rc_create_accumulationbuffer", "rc_advect", "rc_streakline_step", "rc_process_frame",
 ]
 
 
@@ -348,6 +348,25 @@ class Context:
         mask = np.empty((self.h_img, self.w), np.uint8)
         self._chk(self.lib.rc_accumulator_mask(self.h, C.c_int(framecount), _ptr(mask)))
         return mask
+
+    def ingest_bgr(self, bgr, dw, dh, flags=0):
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        sh, sw, _ = bgr.shape
+        gray = np.empty((dh, dw), np.uint8)
+        self._chk(self.lib.rc_ingest_bgr(self.h, _ptr(bgr), C.c_size_t(sw * 3), C.c_int(sw), C.c_int(sh), _ptr(gray),
+                                         C.c_size_t(dw), C.c_int(dw), C.c_int(dh), C.c_int(flags)))
+        return gray
+
+    def submit_frames_bgr(self, bgr_frames, framecount0, outmasks=None, results=None, ingest_flags=0):
+        """bgr_frames: numpy (count, sh, sw, 3) u8.  Asynchronous like process_frames(submit_only=True)."""
+        assert isinstance(bgr_frames, np.ndarray) and bgr_frames.dtype == np.uint8 and bgr_frames.ndim == 4
+        count, sh, sw, _ = bgr_frames.shape
+        n = self.w * self.h_img
+        rc = self._chk(self.lib.rc_submit_frames_bgr(self.h, _ptr(bgr_frames), C.c_size_t(sw * 3), C.c_size_t(sw * sh * 3),
+                                                     C.c_int(sw), C.c_int(sh), C.c_int(count), C.c_int(framecount0),
+                                                     C.c_int(ingest_flags), _ptr(outmasks), C.c_size_t(n),
+                                                     C.byref(results) if results is not None else None))
+        return rc
 
     def wait(self):
         self._chk(self.lib.rc_wait(self.h))

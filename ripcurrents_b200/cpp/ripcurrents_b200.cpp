@@ -61,6 +61,14 @@ void calcOpticalFlowFarneback(const cv::Mat& prev, const cv::Mat& next, cv::Mat&
           "rc_farneback");
 }
 
+void ingest(const cv::Mat& frame_bgr, cv::Mat& gray, cv::Size size)
+{
+    require(frame_bgr.type() == CV_8UC3 && size.width > 0 && size.height > 0, "ingest: CV_8UC3 frame required");
+    if (gray.rows != size.height || gray.cols != size.width || gray.type() != CV_8UC1) gray.create(size.height, size.width, CV_8UC1);
+    check(rc_ingest_bgr(default_context(), frame_bgr.data, frame_bgr.step, frame_bgr.cols, frame_bgr.rows, gray.data, gray.step,
+                        size.width, size.height, 0), "rc_ingest_bgr");
+}
+
 void flowToPolar(const cv::Mat& flow, cv::Mat& polar)
 {
     require(flow.type() == CV_32FC2, "flowToPolar: flow must be CV_32FC2");

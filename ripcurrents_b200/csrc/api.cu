@@ -363,7 +363,7 @@ void rc_destroy(rc_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     free_farneback(c);
-    void* bufs[] = {c->d_tmp, c->d_tmp2, c->d_hist2d, c->d_thr, c->d_acc, c->d_cls, c->d_swin_ring, c->d_swin_avg};
+    void* bufs[] = {c->d_bgr[0], c->d_bgr[1], c->d_tmp, c->d_tmp2, c->d_hist2d, c->d_thr, c->d_acc, c->d_cls, c->d_swin_ring, c->d_swin_avg};
     for (void* p : bufs) if (p) cudaFree(p);
     prof_drain(c);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -1101,17 +1101,22 @@ int rc_create_accumulationbuffer(rc_ctx* c, float* acc, size_t astep, const floa
 }
 
 // ---- fused per-frame / per-batch step -------------------------------------------------------------------------
-int rc_submit_frames(rc_ctx* c, const uint8_t* frames, size_t step, size_t frame_stride, int count, int framecount0,
-                     uint8_t* outmasks, size_t mask_stride, rc_frame_result* results)
+static int submit_impl(rc_ctx* c, const uint8_t* frames, size_t step, size_t frame_stride, int count, int framecount0,
+                       uint8_t* outmasks, size_t mask_stride, rc_frame_result* results, int src_w, int src_h,
+                       int ingest_flags)
 {
+    const bool is_bgr = src_w > 0;
     if (!c) return RC_ERR_INVALID;
     if (!c->configured) return fail(c, RC_ERR_STATE, "rc_flow_configure has not been called%s");
     if (count < 1 || count > c->B) return fail(c, RC_ERR_INVALID, "count must be in [1, max_batch]%s");
     cudaSetDevice(c->device);
     const int w = c->prm.w, h = c->prm.h;
     const size_t n = (size_t)w * h;
-    if (!frames || step < (size_t)w || (count > 1 && frame_stride < step * (size_t)(h - 1) + w))
+    if (!is_bgr && (!frames || step < (size_t)w || (count > 1 && frame_stride < step * (size_t)(h - 1) + w)))
         return fail(c, RC_ERR_INVALID, "bad frame pointer / step / stride%s");
+    if (is_bgr && (!frames || src_h < 1 || step < (size_t)src_w * 3 ||
+                   (count > 1 && frame_stride < step * (size_t)(src_h - 1) + (size_t)src_w * 3)))
+        return fail(c, RC_ERR_INVALID, "bad BGR frame pointer / step / stride%s");
     if (outmasks && count > 1 && mask_stride < n) return fail(c, RC_ERR_INVALID, "mask_stride too small%s");
     int rc = ensure_aggregate(c); if (rc) return rc;
     rc = ensure_accumulator(c, w, h); if (rc) return rc;
@@ -1120,7 +1125,26 @@ int rc_submit_frames(rc_ctx* c, const uint8_t* frames, size_t step, size_t frame
 
     const bool dev_in = is_device_ptr(frames);
     const uint8_t* d = frames; size_t ds = step, dfs = frame_stride;
-    if (!dev_in) {
+    if (is_bgr) {
+        const uint8_t* d_src = frames; size_t sstep = step, sfs = frame_stride;
+        if (!dev_in) {
+            const size_t row = (size_t)src_w * 3, per = row * src_h;
+            rc = ensure(c, &c->d_bgr[slot], &c->d_bgr_cap[slot], per * count); if (rc) return rc;
+            CUDA_TRY(c, cudaStreamWaitEvent(c->s_in, c->ev_compute[slot], 0));
+            if (step == row && (count == 1 || frame_stride == per))
+                CUDA_TRY(c, cudaMemcpyAsync(c->d_bgr[slot], frames, per * count, cudaMemcpyHostToDevice, c->s_in));
+            else
+                for (int j = 0; j < count; j++)
+                    CUDA_TRY(c, cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(c->d_bgr[slot]) + (size_t)j * per, row,
+                                                  frames + (size_t)j * frame_stride, step, row, src_h, cudaMemcpyHostToDevice, c->s_in));
+            CUDA_TRY(c, cudaEventRecord(c->ev_in[slot], c->s_in));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_in[slot], 0));
+            d_src = reinterpret_cast<const uint8_t*>(c->d_bgr[slot]); sstep = row; sfs = per;
+        }
+        rc_launch_ingest_bgr(c, d_src, sstep, sfs, src_w, src_h, c->d_frames[slot], w, n, w, h, count,
+                             (ingest_flags & RC_INGEST_GRAY14) ? 1 : 0);
+        d = c->d_frames[slot]; ds = w; dfs = n;
+    } else if (!dev_in) {
         // H2D on the copy-in stream; it may only overwrite the staging slot once the kernels that read it are done
         CUDA_TRY(c, cudaStreamWaitEvent(c->s_in, c->ev_compute[slot], 0));
         if (step == (size_t)w && (count == 1 || frame_stride == n))
@@ -1167,6 +1191,47 @@ int rc_submit_frames(rc_ctx* c, const uint8_t* frames, size_t step, size_t frame
     }
     c->submitted++;
     return produced;
+}
+
+int rc_submit_frames(rc_ctx* c, const uint8_t* frames, size_t step, size_t frame_stride, int count, int framecount0,
+                     uint8_t* outmasks, size_t mask_stride, rc_frame_result* results)
+{
+    return submit_impl(c, frames, step, frame_stride, count, framecount0, outmasks, mask_stride, results, 0, 0, 0);
+}
+
+int rc_submit_frames_bgr(rc_ctx* c, const uint8_t* bgr_frames, size_t step, size_t frame_stride, int src_w, int src_h,
+                         int count, int framecount0, int ingest_flags, uint8_t* outmasks, size_t mask_stride,
+                         rc_frame_result* results)
+{
+    if (src_w < 1 || src_h < 1) return RC_ERR_INVALID;
+    return submit_impl(c, bgr_frames, step, frame_stride, count, framecount0, outmasks, mask_stride, results, src_w, src_h,
+                       ingest_flags);
+}
+
+int rc_ingest_bgr(rc_ctx* c, const uint8_t* bgr, size_t step, int src_w, int src_h, uint8_t* gray, size_t gray_step,
+                  int dst_w, int dst_h, int flags)
+{
+    if (!c || !bgr || !gray || src_w < 1 || src_h < 1 || dst_w < 1 || dst_h < 1) return RC_ERR_INVALID;
+    if (step < (size_t)src_w * 3 || gray_step < (size_t)dst_w) return fail(c, RC_ERR_INVALID, "bad step%s");
+    cudaSetDevice(c->device);
+    const bool hin = !is_device_ptr(bgr), hout = !is_device_ptr(gray);
+    const uint8_t* d_in = bgr; size_t d_step = step;
+    uint8_t* d_out = gray; size_t o_step = gray_step;
+    if (hin) {
+        const size_t row = (size_t)src_w * 3;
+        int rc = ensure(c, &c->d_tmp, &c->d_tmp_cap, row * src_h); if (rc) return rc;
+        CUDA_TRY(c, cudaMemcpy2DAsync(c->d_tmp, row, bgr, step, row, src_h, cudaMemcpyHostToDevice, c->stream));
+        d_in = reinterpret_cast<const uint8_t*>(c->d_tmp); d_step = row;
+    }
+    if (hout) {
+        int rc = ensure(c, &c->d_tmp2, &c->d_tmp2_cap, (size_t)dst_w * dst_h); if (rc) return rc;
+        d_out = reinterpret_cast<uint8_t*>(c->d_tmp2); o_step = dst_w;
+    }
+    rc_launch_ingest_bgr(c, d_in, d_step, 0, src_w, src_h, d_out, o_step, 0, dst_w, dst_h, 1, (flags & RC_INGEST_GRAY14) ? 1 : 0);
+    CHECK_LAUNCH(c);
+    if (hout) CUDA_TRY(c, cudaMemcpy2DAsync(gray, gray_step, d_out, o_step, dst_w, dst_h, cudaMemcpyDeviceToHost, c->stream));
+    if (hin || hout) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return RC_OK;
 }
 
 int rc_wait(rc_ctx* c)

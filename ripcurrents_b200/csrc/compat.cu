@@ -74,7 +74,62 @@ __global__ void accumulate_kernel(float* __restrict__ acc, size_t astep, const f
     }
 }
 
+// Frame ingest: cv::resize(INTER_LINEAR) of the 8-bit BGR camera frame to the working
+// size followed by cv::cvtColor(COLOR_BGR2GRAY) -- ripcurrents.cpp:209-210, main.cpp:258-259 -- in OpenCV's fixed
+// point (oracle/ingest_oracle.c; bit-exact against cv2 4.13.0): one thread per destination pixel.
+__device__ __forceinline__ void ingest_coef(int d, int sn, double scale, bool clamp_f, int& s0, int& a0, int& a1)
+{
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (clamp_f) {
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+    }
+    s0 = s;
+    a0 = __float2int_rn((1.f - f) * 2048.f);
+    a1 = __float2int_rn(f * 2048.f);
+}
+
+__global__ void __launch_bounds__(256)
+ingest_bgr_kernel(const uint8_t* __restrict__ bgr, size_t step, size_t fstride, int sw, int sh, uint8_t* __restrict__ gray,
+                  size_t gstep, size_t gstride, int dw, int dh, double scale_x, double scale_y, int legacy14)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dw || y >= dh) return;
+    bgr += (size_t)blockIdx.z * fstride;
+    gray += (size_t)blockIdx.z * gstride;
+    int sx, a0, a1, sy, b0, b1;
+    ingest_coef(x, sw, scale_x, true, sx, a0, a1);
+    ingest_coef(y, sh, scale_y, false, sy, b0, b1);
+    const int sx1 = sx + 1 < sw ? sx + 1 : sw - 1;
+    const int sy1 = sy + 1 < 0 ? 0 : (sy + 1 < sh ? sy + 1 : sh - 1);
+    sy = sy < 0 ? 0 : (sy < sh ? sy : sh - 1);
+    const uint8_t* r0 = bgr + (size_t)sy * step;
+    const uint8_t* r1 = bgr + (size_t)sy1 * step;
+    int px[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int h0 = r0[3 * sx + c] * a0 + r0[3 * sx1 + c] * a1;
+        const int h1 = r1[3 * sx + c] * a0 + r1[3 * sx1 + c] * a1;
+        int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        px[c] = v > 255 ? 255 : v;
+    }
+    const int g = legacy14 ? (px[0] * 1868 + px[1] * 9617 + px[2] * 4899 + (1 << 13)) >> 14
+                           : (px[0] * 3735 + px[1] * 19235 + px[2] * 9798 + (1 << 14)) >> 15;
+    gray[(size_t)y * gstep + x] = (uint8_t)g;
+}
+
 }  // namespace
+
+void rc_launch_ingest_bgr(rc_ctx* c, const uint8_t* bgr, size_t step, size_t fstride, int sw, int sh, uint8_t* gray,
+                          size_t gstep, size_t gstride, int dw, int dh, int nb, int legacy14)
+{
+    dim3 g((dw + 31) / 32, (dh + 7) / 8, nb);
+    KScope ks(c, K_MISC, (3.0 * sw * sh + (double)dw * dh) * nb);
+    ingest_bgr_kernel<<<g, 256, 0, c->stream>>>(bgr, step, fstride, sw, sh, gray, gstep, gstride, dw, dh,
+                                               (double)sw / (double)dw, (double)sh / (double)dh, legacy14);
+}
 
 void rc_launch_hist_polar(rc_ctx* c, const float* polar, size_t step, int w, int h, unsigned long long* hist2d)
 {

@@ -111,6 +111,8 @@ struct rc_ctx {
 
     // staging for host frames (double-buffered) and outputs
     uint8_t* d_frames[2] = {nullptr, nullptr};
+    void* d_bgr[2] = {nullptr, nullptr};           // staging for BGR camera frames (rc_submit_frames_bgr), lazily sized
+    size_t d_bgr_cap[2] = {0, 0};
     uint8_t* d_masks[2] = {nullptr, nullptr};
     float* d_thr_batch[2] = {nullptr, nullptr};    // [B][RC_THR_FLOATS] per staging slot
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -201,6 +203,9 @@ void rc_launch_create_flow(rc_ctx* c, float* cur, size_t cstep, float* wc, size_
                            int h, float UPPER, float MID, float LOWER, const float* d_upper2d);
 void rc_launch_accumulate(rc_ctx* c, float* acc, size_t astep, const float* acc2, size_t a2step, float* out, size_t ostep,
                           unsigned char* mask, size_t mstep, int w, int h, int framecount);
+
+void rc_launch_ingest_bgr(rc_ctx* c, const uint8_t* bgr, size_t step, size_t fstride, int sw, int sh, uint8_t* gray,
+                          size_t gstep, size_t gstride, int dw, int dh, int nb, int legacy14);
 
 // ---- advect.cu -------------------------------------------------------------------------------------
 void rc_launch_advect(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float* seeds, size_t n, float dt,

@@ -50,5 +50,17 @@ def main():
                         cv2_version=np.array(cv2.__version__))
 
 
+def ingest():
+    # frame ingest: cv2.resize INTER_LINEAR + cvtColor BGR2GRAY, several size ratios
+    rng = np.random.default_rng(5)
+    out = {}
+    for i, (sw, sh, dw, dh) in enumerate([(320, 180, 160, 120), (200, 150, 200, 150), (131, 97, 64, 48), (100, 80, 160, 120)]):
+        img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        g = cv2.cvtColor(cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY)
+        out["bgr%d" % i] = img; out["gray%d" % i] = g
+    np.savez_compressed(os.path.join(HERE, "ingest.npz"), cv2_version=np.array(cv2.__version__), **out)
+
+
 if __name__ == "__main__":
     main()
+    ingest()

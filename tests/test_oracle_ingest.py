@@ -1,0 +1,24 @@
+"""Pins oracle/ingest_oracle.c bit-exactly to OpenCV (cv2 4.13.0 fixtures + live): resize(INTER_LINEAR) followed by
+cvtColor(BGR2GRAY), the two calls that precede the flow in every frame loop of the reference (ripcurrents.cpp:209-210)."""
+import os
+
+import numpy as np
+import pytest
+
+from util import GOLDEN
+
+
+def test_ingest_golden(oracle):
+    z = np.load(os.path.join(GOLDEN, "ingest.npz"))
+    for i in range(4):
+        g = z["gray%d" % i]
+        assert np.array_equal(oracle.ingest_bgr(z["bgr%d" % i], g.shape[1], g.shape[0]), g), i
+
+
+def test_ingest_live(oracle):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, (270, 480, 3), dtype=np.uint8)
+    for dw, dh in [(160, 120), (480, 270), (333, 211), (600, 400), (480, 300)]:
+        ref = cv2.cvtColor(cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY)
+        assert np.array_equal(oracle.ingest_bgr(img, dw, dh), ref)
