@@ -1088,7 +1088,7 @@ flow_layer_kernel(FlowArgs a)
 // ---------------------------------------------------------------------------------------------------
 template <int NT, bool BOX>
 __global__ void __launch_bounds__(256)
-flow_strip_kernel(FlowArgs a, int SEG)
+flow_strip_kernel(FlowArgs a, int SEG, int only_border)
 {
     constexpr int UW = 32 - 2 * NT;
     __shared__ unsigned int sH[RC_HIST_CELLS];
@@ -1103,6 +1103,9 @@ flow_strip_kernel(FlowArgs a, int SEG)
     }
     const int sx0 = (blockIdx.x * 8 + wrp) * UW;
     const int y0 = blockIdx.y * SEG;
+    // segments strictly inside the image are handled by flow_strip2_kernel when `only_border` is set
+    const bool interior_seg = NT == 2 && y0 - 2 >= 0 && y0 + SEG + 2 <= h;
+    if (only_border && interior_seg) return;
     if (sx0 < w) {
         const int xv = sx0 - NT + lane;
         const int x = clampi(xv, 0, w - 1);
@@ -1190,6 +1193,115 @@ flow_strip_kernel(FlowArgs a, int SEG)
                 if (col_out) outp[yo * w + xv] = f;
                 if (do_hist) {
                     const int key = col_out ? hist_key_fast(f.x, f.y) : -1;
+                    const unsigned peers = __match_any_sync(0xffffffffu, key);
+                    if (key >= 0 && (int)(__ffs(peers) - 1) == lane) {
+                        if (atomicAdd(&sH[key], __popc(peers)) == 0) {
+                            const int slot = atomicAdd(&sNKeys, 1);
+                            if (slot < 256) sKeys[slot] = (unsigned short)key;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (do_hist) {
+        __syncthreads();
+        unsigned int* dst = a.hist_delta + (size_t)j * RC_HIST_CELLS;
+        const int nk = sNKeys;
+        if (nk <= 256) {
+            if (tid < nk) { const int k = sKeys[tid]; atomicAdd(&dst[k], sH[k]); }
+        } else {
+            for (int i = tid; i < RC_HIST_CELLS; i += 256)
+                if (sH[i]) atomicAdd(&dst[i], sH[i]);
+        }
+    }
+}
+
+// Software-pipelined strip kernel for the reference default (2 iterations), segments strictly inside the image:
+// the gathers of BOTH updateMatrices evaluations are issued one row before they are consumed, so no load latency
+// sits on the per-row dependency chain (M0[v] -> flow1[v-1] -> M1[v-1] -> flow2[v-2]).  Row v of the loop:
+//   finish M0[v] (gathers issued at v-1), issue the gathers of M0[v+1];
+//   flow1[v-1] from M0[v-2..v]; finish M1[v-2] (gathers issued at v-1), issue those of M1[v-1] with flow1[v-1];
+//   flow2[v-3] from M1[v-4..v-2] -> output row v-3.
+// Segments touching the top / bottom border run in flow_strip_kernel (replicate handling), launched alongside.
+template <bool BOX>
+__global__ void __launch_bounds__(256)
+flow_strip2_kernel(FlowArgs a, int SEG)
+{
+    constexpr int NT = 2, UW = 32 - 2 * NT;
+    __shared__ unsigned int sH[RC_HIST_CELLS];
+    __shared__ unsigned short sKeys[256];
+    __shared__ int sNKeys;
+    const int w = a.w, h = a.h, j = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, pitch = a.pitch;
+    const int y0 = blockIdx.y * SEG;
+    if (!(y0 - 2 >= 0 && y0 + SEG + 2 <= h)) return;            // border segment: flow_strip_kernel's job
+    const bool do_hist = a.hist_delta != nullptr;
+    if (do_hist) {
+        for (int i = tid; i < RC_HIST_CELLS; i += 256) sH[i] = 0;
+        if (tid == 0) sNKeys = 0;
+        __syncthreads();
+    }
+    const int sx0 = (blockIdx.x * 8 + wrp) * UW;
+    if (sx0 < w) {
+        const int xv = sx0 - NT + lane;
+        const int x = clampi(xv, 0, w - 1);
+        const bool col_out = lane >= NT && lane < 32 - NT && xv < w;
+        const bool need_fix = (sx0 - NT < 0) || (sx0 - NT + 31 >= w);
+        const int src_lane = x - (sx0 - NT);
+        const RView R0 = rview(a.R0(j), a.plane), R1 = rview(a.R1(j), a.plane);
+        const float2* coarse = a.coarse ? reinterpret_cast<const float2*>(a.coarse + (size_t)j * a.coarse_stride) : nullptr;
+        int csx = 0; float cfx = 0.f;
+        if (coarse) resize_coef(x, a.cw, a.sxs, csx, cfx);
+        const float k0 = a.win.k[0], k1 = a.win.k[1], ps = a.win.post_scale;
+        float2* outp = reinterpret_cast<float2*>(a.out(j));
+
+        UMIn p0, p1;                      // gathers in flight for level 0 (row v+1) and level 1 (row v-1)
+        auto issue0 = [&](int r) {
+            float2 fi = make_float2(0.f, 0.f);
+            if (coarse) {
+                int csy; float cfy;
+                resize_coef(r, a.ch, a.sys, csy, cfy);
+                fi = upsample_flow_tab(coarse, a.cw, a.ch, csx, cfx, csy, cfy, a.fscale);
+            }
+            um_load(p0, x, r, fi.x, fi.y, w, h, R0, R1, pitch);
+        };
+        float A0[5], B0[5], A1[5], B1[5];
+#pragma unroll
+        for (int c = 0; c < 5; c++) { A0[c] = B0[c] = A1[c] = B1[c] = 0.f; }
+        const int v0 = y0 - 2, vend = y0 + SEG + 2;               // rows v0 .. vend inclusive (vend <= h - ... + 0)
+        issue0(v0);
+        um_load(p1, x, v0, 0.f, 0.f, w, h, R0, R1, pitch);         // dummy, keeps the pipeline uniform (result unused)
+#pragma unroll 1
+        for (int v = v0; v <= vend; v++) {
+            float C0[5], C1[5];
+            um_finish(p0, x, v, w, h, C0);                         // M0[v]
+            if (v < vend) issue0(min(v + 1, h - 1));
+            um_finish(p1, x, max(v - 2, 0), w, h, C1);             // M1[v-2] (garbage during warm-up, never output)
+            float sv[5];
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                const float vs = BOX ? B0[c] + (A0[c] + C0[c]) : fmaf(A0[c] + C0[c], k1, B0[c] * k0);
+                const float lft = __shfl_up_sync(0xffffffffu, vs, 1), rgt = __shfl_down_sync(0xffffffffu, vs, 1);
+                sv[c] = (BOX ? vs + (lft + rgt) : fmaf(lft + rgt, k1, vs * k0)) * ps;
+                A0[c] = B0[c]; B0[c] = C0[c];
+            }
+            float2 f1 = solve_fast(sv[0], sv[1], sv[2], sv[3], sv[4]);          // flow1[v-1]
+            if (need_fix) { f1.x = __shfl_sync(0xffffffffu, f1.x, src_lane); f1.y = __shfl_sync(0xffffffffu, f1.y, src_lane); }
+            if (!(fabsf(f1.x) < 1e18f) || !(fabsf(f1.y) < 1e18f)) f1 = make_float2(0.f, 0.f);   // warm-up rows / edge lanes only
+            um_load(p1, x, max(v - 1, 0), f1.x, f1.y, w, h, R0, R1, pitch);     // gathers of M1[v-1]
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                const float vs = BOX ? B1[c] + (A1[c] + C1[c]) : fmaf(A1[c] + C1[c], k1, B1[c] * k0);
+                const float lft = __shfl_up_sync(0xffffffffu, vs, 1), rgt = __shfl_down_sync(0xffffffffu, vs, 1);
+                sv[c] = (BOX ? vs + (lft + rgt) : fmaf(lft + rgt, k1, vs * k0)) * ps;
+                A1[c] = B1[c]; B1[c] = C1[c];
+            }
+            const float2 f2 = solve_fast(sv[0], sv[1], sv[2], sv[3], sv[4]);    // flow2[v-3]
+            const int yo = v - 3;
+            if (yo >= y0 && yo < y0 + SEG) {                                     // warp-uniform
+                if (col_out) outp[yo * w + xv] = f2;
+                if (do_hist) {
+                    const int key = col_out ? hist_key_fast(f2.x, f2.y) : -1;
                     const unsigned peers = __match_any_sync(0xffffffffu, key);
                     if (key >= 0 && (int)(__ffs(peers) - 1) == lane) {
                         if (atomicAdd(&sH[key], __popc(peers)) == 0) {
@@ -1395,19 +1507,33 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         if (fused_ok) {
             dim3 g((L.w + 31) / 32, (L.h + 31) / 32, nb);
             KScope ks(c, K_FLOW_LAYER, (a.coarse ? 50.0 : 48.0) * npx);
-            static const int use_strip = getenv("RC_FLOW_STRIP") ? 1 : 0;     // A/B switch: register/shuffle strip kernel
+            static const int use_strip = getenv("RC_FLOW_STRIP") ? atoi(getenv("RC_FLOW_STRIP")) : 0;   // A/B switch
+            if (use_strip == 2 && T == 2) {
+                const int SEG = L.h >= 512 ? 64 : 32;
+                const int UW = 32 - 2 * T;
+                dim3 gs(((L.w + UW - 1) / UW + 7) / 8, (L.h + SEG - 1) / SEG, nb);
+                if (!c->win.gaussian) {
+                    flow_strip2_kernel<true><<<gs, 256, 0, c->stream>>>(a, SEG);
+                    flow_strip_kernel<2, true><<<gs, 256, 0, c->stream>>>(a, SEG, 1);
+                } else {
+                    flow_strip2_kernel<false><<<gs, 256, 0, c->stream>>>(a, SEG);
+                    flow_strip_kernel<2, false><<<gs, 256, 0, c->stream>>>(a, SEG, 1);
+                }
+                c->launches += 1;
+                continue;
+            }
             if (use_strip) {
                 const int SEG = L.h >= 512 ? 64 : 32;
                 const int UW = 32 - 2 * T;
                 dim3 gs(((L.w + UW - 1) / UW + 7) / 8, (L.h + SEG - 1) / SEG, nb);
                 if (!c->win.gaussian) {
-                    if (T == 1) flow_strip_kernel<1, true><<<gs, 256, 0, c->stream>>>(a, SEG);
-                    else if (T == 2) flow_strip_kernel<2, true><<<gs, 256, 0, c->stream>>>(a, SEG);
-                    else flow_strip_kernel<3, true><<<gs, 256, 0, c->stream>>>(a, SEG);
+                    if (T == 1) flow_strip_kernel<1, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0);
+                    else if (T == 2) flow_strip_kernel<2, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0);
+                    else flow_strip_kernel<3, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0);
                 } else {
-                    if (T == 1) flow_strip_kernel<1, false><<<gs, 256, 0, c->stream>>>(a, SEG);
-                    else if (T == 2) flow_strip_kernel<2, false><<<gs, 256, 0, c->stream>>>(a, SEG);
-                    else flow_strip_kernel<3, false><<<gs, 256, 0, c->stream>>>(a, SEG);
+                    if (T == 1) flow_strip_kernel<1, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0);
+                    else if (T == 2) flow_strip_kernel<2, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0);
+                    else flow_strip_kernel<3, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0);
                 }
                 continue;
             }
