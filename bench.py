@@ -212,7 +212,26 @@ class DevArr:
         self.__cuda_array_interface__ = {"data": (ptr, False), "shape": shape, "typestr": typestr, "version": 2}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank to the CPU cores NVML reports as local to its GPU, so that the pinned host buffers it allocates
+    next (first touch) and its copy submissions stay on the GPU's NUMA node.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_ours(args, rank, world, local_rank):
+    ncpu_local = bind_to_gpu_numa_node(local_rank)
     import torch
     import torch.distributed as dist
     from ripcurrents_b200 import Context, synth
@@ -369,6 +388,7 @@ def run_ours(args, rank, world, local_rank):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": FRAMES_PER_STEP * W * H,
                         "d2h_bytes_per_step": FRAMES_PER_STEP * (W * H + 320), "ms_per_step": ms_e2e / args.steps,
                         "api": "rc_submit_frames(16 pinned host frames) -> 16 outmasks + threshold records on the host, rc_wait"},
+                "host_binding": "rank pinned to %d GPU-local cores (NVML affinity)" % ncpu_local if ncpu_local else "none",
                 "gpu_launches": int(launches), "clocks": sampler.summary(t_region0, t_region1 + 0.05), "roofline": roofline, "kernels": kernels,
                 "check": {"last_UPPER": float(h_results[(state["step"] - 1) & 1][FRAMES_PER_STEP - 1].UPPER),
                           "histsum": int(h_results[(state["step"] - 1) & 1][FRAMES_PER_STEP - 1].histsum)}}

@@ -1400,10 +1400,10 @@ static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
     constexpr int TX = 64, TY = 32;
     const int n = c->poly.n;
     const size_t smem = sizeof(float) * ((size_t)(TY + 2 * n) * (TX + 2 * n) + 3 * (size_t)TY * (TX + 2 * n));
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[64] = {0};      // cudaFuncSetAttribute is per device
+    if (smem > configured[c->device & 63]) {
         cudaFuncSetAttribute(polyexp_strict_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+        configured[c->device & 63] = smem;
     }
     dim3 g((L.w + TX - 1) / TX, (L.h + TY - 1) / TY, nb);
     polyexp_strict_kernel<TX, TY><<<g, 256, smem, c->stream>>>(L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot,
@@ -1453,10 +1453,10 @@ void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fs
                    4 * (size_t)a.SRW;
             if (smem <= 100 * 1024) break;
         }
-        static size_t configured = 0;
-        if (smem > configured && smem > 48 * 1024) {
+        static size_t configured[64] = {0};  // per device
+        if (smem > configured[c->device & 63] && smem > 48 * 1024) {
             cudaFuncSetAttribute(pyr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = smem;
+            configured[c->device & 63] = smem;
         }
         {
             dim3 g((L.w + a.TXD - 1) / a.TXD, (L.h + a.TYD - 1) / a.TYD, nb);
@@ -1558,11 +1558,11 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         const int m = c->win.m;
         const size_t tsm = sizeof(float) * ((size_t)(16 + 2 * m) * (64 + 2 * m) + 16 * (size_t)(64 + 2 * m));
         if (tiled && tsm > 48 * 1024) {
-            static size_t configured = 0;
-            if (tsm > configured) {
+            static size_t configured[64] = {0};   // per device
+            if (tsm > configured[c->device & 63]) {
                 cudaFuncSetAttribute(flow_iter_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
                 cudaFuncSetAttribute(flow_iter_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-                configured = tsm;
+                configured[c->device & 63] = tsm;
             }
         }
         dim3 gt((L.w + 63) / 64, (L.h + 15) / 16, nb);
