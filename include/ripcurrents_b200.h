@@ -231,6 +231,13 @@ int rc_submit_frames_bgr(rc_ctx* ctx, const uint8_t* bgr_frames, size_t step, si
                          int count, int framecount0, int ingest_flags, uint8_t* outmasks, size_t mask_stride,
                          rc_frame_result* results);
 
+/* ---- mask clean-up ---------------------------------------------------------------
+ * create_edges (ripcurrents_module.cpp:216-220 == ripcurrents.cpp:494-496): dilate(outmask, 5x5 ellipse) followed by
+ * morphologyEx(MORPH_GRADIENT) with the same element; bit-exact against cv2.  `count` masks `mask_stride` bytes
+ * apart are processed in one launch; edges may alias masks only when count == 1 and the pointers are on the host. */
+int rc_mask_edges(rc_ctx* ctx, const uint8_t* masks, size_t mask_step, size_t mask_stride, int w, int h, int count,
+                  uint8_t* edges, size_t edges_step, size_t edges_stride);
+
 /* ---- fused per-frame step (what main()'s loop body does between video.read and imshow) ----------- */
 
 /* rc_flow_push + rc_polar_hist + rc_thresholds + rc_classify_accumulate (+ rc_window_update when a window is

@@ -56,3 +56,43 @@ void rc_oracle_ingest_bgr(const uint8_t* bgr, size_t step, int sw, int sh, uint8
         }
     }
 }
+
+/*
+ * Mask clean-up: create_edges, ripcurrents_module.cpp:216-220 == ripcurrents.cpp:494-496:
+ *     morph_window = getStructuringElement(MORPH_ELLIPSE, Size(5,5));
+ *     dilate(outmask, outmask, morph_window);
+ *     morphologyEx(outmask, outmask, MORPH_GRADIENT, morph_window);     // dilation - erosion
+ * OpenCV's 5x5 ellipse is {..X.., XXXXX, XXXXX, XXXXX, ..X..}; taps outside the image are ignored
+ * (BORDER_CONSTANT with morphologyDefaultBorderValue).  Pinned bit-exactly against cv2 in tests/test_oracle_ingest.py.
+ */
+static const unsigned char ELL5[5][5] = {{0, 0, 1, 0, 0}, {1, 1, 1, 1, 1}, {1, 1, 1, 1, 1}, {1, 1, 1, 1, 1}, {0, 0, 1, 0, 0}};
+
+static void morph5(const uint8_t* in, int w, int h, int dilate, uint8_t* out)
+{
+    int x, y, dx, dy;
+    for (y = 0; y < h; y++)
+        for (x = 0; x < w; x++) {
+            int v = dilate ? 0 : 255;
+            for (dy = -2; dy <= 2; dy++)
+                for (dx = -2; dx <= 2; dx++) {
+                    int xx = x + dx, yy = y + dy, p;
+                    if (!ELL5[dy + 2][dx + 2] || xx < 0 || yy < 0 || xx >= w || yy >= h) continue;
+                    p = in[(size_t)yy * w + xx];
+                    v = dilate ? (p > v ? p : v) : (p < v ? p : v);
+                }
+            out[(size_t)y * w + x] = (uint8_t)v;
+        }
+}
+
+void rc_oracle_edges(const uint8_t* mask, int w, int h, uint8_t* edges)
+{
+    size_t i, n = (size_t)w * h;
+    uint8_t* d = (uint8_t*)malloc(n);
+    uint8_t* dd = (uint8_t*)malloc(n);
+    uint8_t* de = (uint8_t*)malloc(n);
+    morph5(mask, w, h, 1, d);
+    morph5(d, w, h, 1, dd);
+    morph5(d, w, h, 0, de);
+    for (i = 0; i < n; i++) edges[i] = (uint8_t)(dd[i] - de[i]);
+    free(d); free(dd); free(de);
+}

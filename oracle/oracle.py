@@ -210,3 +210,12 @@ def ingest_bgr(bgr, dw, dh, legacy14=False):
     lib().rc_oracle_ingest_bgr(_p(bgr), C.c_size_t(sw * 3), C.c_int(sw), C.c_int(sh), _p(out), C.c_int(dw), C.c_int(dh),
                                C.c_int(1 if legacy14 else 0))
     return out
+
+
+def edges(mask):
+    """create_edges (ripcurrents_module.cpp:216-220): 5x5 elliptical dilate + morphological gradient."""
+    mask = np.ascontiguousarray(mask, np.uint8)
+    h, w = mask.shape
+    out = np.empty((h, w), np.uint8)
+    lib().rc_oracle_edges(_p(mask), C.c_int(w), C.c_int(h), _p(out))
+    return out

@@ -23,7 +23,7 @@ SYMBOLS = [
     "rc_hist_reset", "rc_polar_hist", "rc_hist_get", "rc_hist_add", "rc_hist_device", "rc_cart_to_polar",
     "rc_thresholds", "rc_accumulator_reset", "rc_classify_accumulate", "rc_accumulator_get",
     "rc_accumulator_device", "rc_window_configure", "rc_window_update", "rc_window_get", "rc_window_device",
-    "rc_subtract_mean", "rc_batch_hist", "rc_aggregate_last", "rc_accumulator_mask", "rc_ingest_bgr", "rc_submit_frames_bgr", "rc_hist_from_polar", "rc_create_flow", "rc_create_accumulationbuffer", "rc_advect", "rc_streakline_step", "rc_process_frame",
+    "rc_subtract_mean", "rc_batch_hist", "rc_aggregate_last", "rc_accumulator_mask", "rc_mask_edges", "rc_ingest_bgr", "rc_submit_frames_bgr", "rc_hist_from_polar", "rc_create_flow", "rc_create_accumulationbuffer", "rc_advect", "rc_streakline_step", "rc_process_frame",
 ]
 
 
@@ -348,6 +348,17 @@ class Context:
         mask = np.empty((self.h_img, self.w), np.uint8)
         self._chk(self.lib.rc_accumulator_mask(self.h, C.c_int(framecount), _ptr(mask)))
         return mask
+
+    def mask_edges(self, masks):
+        """masks: (h,w) or (count,h,w) u8 -> edges of the same shape (create_edges)."""
+        masks = np.ascontiguousarray(masks, np.uint8)
+        shp = masks.shape
+        m3 = masks.reshape((-1,) + shp[-2:])
+        count, h, w = m3.shape
+        out = np.empty_like(m3)
+        self._chk(self.lib.rc_mask_edges(self.h, _ptr(m3), C.c_size_t(w), C.c_size_t(w * h), C.c_int(w), C.c_int(h),
+                                         C.c_int(count), _ptr(out), C.c_size_t(w), C.c_size_t(w * h)))
+        return out.reshape(shp)
 
     def ingest_bgr(self, bgr, dw, dh, flags=0):
         bgr = np.ascontiguousarray(bgr, np.uint8)

@@ -60,6 +60,7 @@ void create_histogram(cv::Mat current, int hist[HIST_BINS], int& histsum, int hi
 void create_flow(cv::Mat current, cv::Mat waterclass, cv::Mat accumulator2, float UPPER, float MID, float LOWER,
                  float UPPER2d[HIST_DIRECTIONS]);
 void create_accumulationbuffer(cv::Mat& accumulator, cv::Mat accumulator2, cv::Mat& out, cv::Mat outmask, int framecount);
+void create_edges(cv::Mat& outmask);
 void get_delta(Pixel2* pt, int xoffset, int yoffset, cv::Mat flow, float dt, float UPPER);
 void subtructAverage(cv::Mat& current);
 

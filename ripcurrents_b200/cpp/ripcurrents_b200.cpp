@@ -232,6 +232,13 @@ void create_accumulationbuffer(cv::Mat& accumulator, cv::Mat accumulator2, cv::M
           "rc_create_accumulationbuffer");
 }
 
+void create_edges(cv::Mat& outmask)
+{
+    require(outmask.type() == CV_8UC1, "create_edges: CV_8UC1 mask required");
+    check(rc_mask_edges(rc::default_context(), outmask.data, outmask.step, 0, outmask.cols, outmask.rows, 1, outmask.data,
+                        outmask.step, 0), "rc_mask_edges");
+}
+
 void subtructAverage(cv::Mat& current)
 {
     require(current.type() == CV_32FC2, "subtructAverage: CV_32FC2 flow required");

@@ -1100,6 +1100,39 @@ int rc_create_accumulationbuffer(rc_ctx* c, float* acc, size_t astep, const floa
     return RC_OK;
 }
 
+int rc_mask_edges(rc_ctx* c, const uint8_t* masks, size_t mask_step, size_t mask_stride, int w, int h, int count,
+                  uint8_t* edges, size_t edges_step, size_t edges_stride)
+{
+    if (!c || !masks || !edges || w < 1 || h < 1 || count < 1 || mask_step < (size_t)w || edges_step < (size_t)w)
+        return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    const size_t n = (size_t)w * h;
+    const bool hin = !is_device_ptr(masks), hout = !is_device_ptr(edges);
+    const uint8_t* d_in = masks; size_t istep = mask_step, istride = mask_stride;
+    uint8_t* d_out = edges; size_t ostep = edges_step, ostride = edges_stride;
+    if (hin) {
+        int rc = ensure(c, &c->d_tmp, &c->d_tmp_cap, n * count); if (rc) return rc;
+        for (int j = 0; j < count; j++)
+            CUDA_TRY(c, cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(c->d_tmp) + (size_t)j * n, w, masks + (size_t)j * mask_stride,
+                                          mask_step, w, h, cudaMemcpyHostToDevice, c->stream));
+        d_in = reinterpret_cast<const uint8_t*>(c->d_tmp); istep = w; istride = n;
+    }
+    if (hout) {
+        int rc = ensure(c, &c->d_tmp2, &c->d_tmp2_cap, n * count); if (rc) return rc;
+        d_out = reinterpret_cast<uint8_t*>(c->d_tmp2); ostep = w; ostride = n;
+    } else if (d_out == d_in) {
+        return fail(c, RC_ERR_INVALID, "in-place edges need host pointers%s");
+    }
+    rc_launch_edges(c, d_in, istep, istride, w, h, d_out, ostep, ostride, count);
+    CHECK_LAUNCH(c);
+    if (hout)
+        for (int j = 0; j < count; j++)
+            CUDA_TRY(c, cudaMemcpy2DAsync(edges + (size_t)j * edges_stride, edges_step, d_out + (size_t)j * n, w, w, h,
+                                          cudaMemcpyDeviceToHost, c->stream));
+    if (hin || hout) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return RC_OK;
+}
+
 // ---- fused per-frame / per-batch step -------------------------------------------------------------------------
 static int submit_impl(rc_ctx* c, const uint8_t* frames, size_t step, size_t frame_stride, int count, int framecount0,
                        uint8_t* outmasks, size_t mask_stride, rc_frame_result* results, int src_w, int src_h,

@@ -120,7 +120,66 @@ ingest_bgr_kernel(const uint8_t* __restrict__ bgr, size_t step, size_t fstride, 
     gray[(size_t)y * gstep + x] = (uint8_t)g;
 }
 
+// Mask clean-up: create_edges, ripcurrents_module.cpp:216-220 -- dilate with OpenCV's
+// 5x5 ellipse, then morphological gradient (dilate - erode) with the same element; taps outside the image are ignored.
+// One 32x32 tile per CTA, both stages in shared memory (halo 4), any number of masks per launch (blockIdx.z).
+__device__ __forceinline__ bool ell5(int dx, int dy) { return dy == -2 || dy == 2 ? dx == 0 : true; }
+
+__global__ void __launch_bounds__(256)
+edges_kernel(const uint8_t* __restrict__ mask, size_t step, size_t stride, int w, int h, uint8_t* __restrict__ out,
+             size_t ostep, size_t ostride)
+{
+    __shared__ uint8_t sIn[40][40];
+    __shared__ uint8_t sD[36][36];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32, tid = threadIdx.x;
+    mask += (size_t)blockIdx.z * stride;
+    out += (size_t)blockIdx.z * ostride;
+    for (int i = tid; i < 40 * 40; i += 256) {
+        const int cy = i / 40, cx = i - cy * 40, x = x0 - 4 + cx, y = y0 - 4 + cy;
+        sIn[cy][cx] = (x >= 0 && y >= 0 && x < w && y < h) ? mask[(size_t)y * step + x] : 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < 36 * 36; i += 256) {
+        const int cy = i / 36, cx = i - cy * 36, x = x0 - 2 + cx, y = y0 - 2 + cy;
+        int v = 0;
+        if (x >= 0 && y >= 0 && x < w && y < h) {
+#pragma unroll
+            for (int dy = -2; dy <= 2; dy++)
+#pragma unroll
+                for (int dx = -2; dx <= 2; dx++)
+                    if (ell5(dx, dy)) v = max(v, (int)sIn[cy + 2 + dy][cx + 2 + dx]);
+        }
+        sD[cy][cx] = (uint8_t)v;
+    }
+    __syncthreads();
+    for (int i = tid; i < 32 * 32; i += 256) {
+        const int cy = i >> 5, cx = i & 31, x = x0 + cx, y = y0 + cy;
+        if (x >= w || y >= h) continue;
+        int dd = 0, de = 255;
+#pragma unroll
+        for (int dy = -2; dy <= 2; dy++)
+#pragma unroll
+            for (int dx = -2; dx <= 2; dx++)
+                if (ell5(dx, dy)) {
+                    const int xx = x + dx, yy = y + dy;
+                    if (xx >= 0 && yy >= 0 && xx < w && yy < h) {
+                        const int p = sD[cy + 2 + dy][cx + 2 + dx];
+                        dd = max(dd, p); de = min(de, p);
+                    }
+                }
+        out[(size_t)y * ostep + x] = (uint8_t)(dd - de);
+    }
+}
+
 }  // namespace
+
+void rc_launch_edges(rc_ctx* c, const uint8_t* mask, size_t step, size_t stride, int w, int h, uint8_t* out, size_t ostep,
+                     size_t ostride, int nb)
+{
+    dim3 g((w + 31) / 32, (h + 31) / 32, nb);
+    KScope ks(c, K_MISC, 2.0 * w * h * nb);
+    edges_kernel<<<g, 256, 0, c->stream>>>(mask, step, stride, w, h, out, ostep, ostride);
+}
 
 void rc_launch_ingest_bgr(rc_ctx* c, const uint8_t* bgr, size_t step, size_t fstride, int sw, int sh, uint8_t* gray,
                           size_t gstep, size_t gstride, int dw, int dh, int nb, int legacy14)

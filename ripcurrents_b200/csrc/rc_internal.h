@@ -207,6 +207,9 @@ void rc_launch_accumulate(rc_ctx* c, float* acc, size_t astep, const float* acc2
 void rc_launch_ingest_bgr(rc_ctx* c, const uint8_t* bgr, size_t step, size_t fstride, int sw, int sh, uint8_t* gray,
                           size_t gstep, size_t gstride, int dw, int dh, int nb, int legacy14);
 
+void rc_launch_edges(rc_ctx* c, const uint8_t* mask, size_t step, size_t stride, int w, int h, uint8_t* out, size_t ostep,
+                     size_t ostride, int nb);
+
 // ---- advect.cu -------------------------------------------------------------------------------------
 void rc_launch_advect(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float* seeds, size_t n, float dt,
                       int iterations, float upper, int variant, float* dist, const int32_t* home);

@@ -63,3 +63,17 @@ def test_bgr_fed_pipeline_equals_gray_fed(oracle):
     assert ra == rb and np.array_equal(ma[1:], mb[1:])
     assert np.array_equal(a.flow_host(), b.flow_host())
     a.close(); b.close()
+
+
+def test_mask_edges_bit_exact(ctx, oracle):
+    """create_edges (ripcurrents_module.cpp:216-220): batch of masks, ragged size, border pixels set."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(6)
+    for shape, thr in [((5, 1080, 1920), 0.97), ((3, 97, 131), 0.8), ((1, 32, 32), 0.5)]:
+        m = (rng.random(shape) > thr).astype(np.uint8) * 255
+        m[:, 0, :7] = 255; m[:, -1, -2:] = 255; m[:, :, 0] |= m[:, :, 1]
+        got = ctx.mask_edges(m)
+        k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (5, 5))
+        for i in range(shape[0]):
+            assert np.array_equal(got[i], oracle.edges(m[i])), (shape, i)
+            assert np.array_equal(got[i], cv2.morphologyEx(cv2.dilate(m[i], k), cv2.MORPH_GRADIENT, k)), (shape, i)

@@ -22,3 +22,16 @@ def test_ingest_live(oracle):
     for dw, dh in [(160, 120), (480, 270), (333, 211), (600, 400), (480, 300)]:
         ref = cv2.cvtColor(cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY)
         assert np.array_equal(oracle.ingest_bgr(img, dw, dh), ref)
+
+
+def test_edges_vs_cv2(oracle):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for shape, thr in [((120, 160), 0.93), ((33, 47), 0.8), ((64, 64), 0.995)]:
+        m = (rng.random(shape) > thr).astype(np.uint8) * 255
+        m[0, :5] = 255; m[-1, -3:] = 255
+        k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (5, 5))
+        ref = cv2.morphologyEx(cv2.dilate(m, k), cv2.MORPH_GRADIENT, k)
+        assert np.array_equal(oracle.edges(m), ref)
+    assert not oracle.edges(np.zeros((20, 30), np.uint8)).any()
+    assert not oracle.edges(np.full((20, 30), 255, np.uint8)).any()      # all-wave mask has no edges
