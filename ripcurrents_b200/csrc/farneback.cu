@@ -746,8 +746,8 @@ flow_iter_tiled_kernel(FlowArgs a, int mi)
     const int m = a.win.m, WP = TX + 2 * m, HP = TY + 2 * m;
     float* sIn = fsm;                   // [HP][WP]
     float* sV = fsm + HP * WP;          // [TY][WP]
-    const int w = a.w, h = a.h, j = blockIdx.z, tid = threadIdx.x;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int w = a.w, h = a.h, j = blockIdx.x, tid = threadIdx.x;       // grid = (pairs, tiles_x, tiles_y)
+    const int x0 = blockIdx.y * TX, y0 = blockIdx.z * TY;
     const float* Min = a.M + (size_t)j * a.m_stride + (size_t)mi * 5 * a.plane;
     const int lane = tid & 31, wrp = tid >> 5;
     const int tx = tid & 63, tyb = tid >> 6;          // this thread's pixels: (tx, tyb + 4*i), i = 0..3
@@ -815,8 +815,8 @@ flow_iter_tiled_m_kernel(FlowArgs a, int mi)
     __shared__ unsigned int sH[FUSE ? 1 : RC_HIST_CELLS];
     __shared__ unsigned short sKeys[FUSE ? 1 : 256];
     __shared__ int sNKeys;
-    const int w = a.w, h = a.h, j = blockIdx.z, tid = threadIdx.x;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int w = a.w, h = a.h, j = blockIdx.x, tid = threadIdx.x;       // grid = (pairs, tiles_x, tiles_y)
+    const int x0 = blockIdx.y * TX, y0 = blockIdx.z * TY;
     const float* Min = a.M + (size_t)j * a.m_stride + (size_t)mi * 5 * a.plane;
     const int lane = tid & 31, wrp = tid >> 5;
     const int row = tid >> 4, xg = tid & 15;            // horizontal-pass role: pixels (4*xg .. 4*xg+3, row)
@@ -952,8 +952,10 @@ flow_layer_kernel(FlowArgs a)
     __shared__ int sNKeys;
     __shared__ int sSX[RS], sSY[RS];
     __shared__ float sFX[RS], sFY[RS];
-    const int w = a.w, h = a.h, j = blockIdx.z, tid = threadIdx.x, pitch = a.pitch;
-    const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
+    // grid = (pairs, tiles_x, tiles_y): the pair index varies fastest, so the CTAs that read frame t+1's expansion as
+    // R1 (pair t) and as R0 (pair t+1) run back to back and the second read hits L2
+    const int w = a.w, h = a.h, j = blockIdx.x, tid = threadIdx.x, pitch = a.pitch;
+    const int x0 = blockIdx.y * T, y0 = blockIdx.z * T;
     const RView R0 = rview(a.R0(j), a.plane), R1 = rview(a.R1(j), a.plane);
     const bool do_hist = a.hist_delta != nullptr;
     if (do_hist) {
@@ -1086,23 +1088,26 @@ flow_layer_kernel(FlowArgs a)
 // are evaluated at clamped pixels, deeper levels duplicate their first/last real row and copy the flow of the
 // clamped column before updateMatrices, which reproduces M at the clamped pixel exactly.
 // ---------------------------------------------------------------------------------------------------
-template <int NT, bool BOX>
-__global__ void __launch_bounds__(256)
+// PF: level-0 gathers prefetched one row ahead (registers).  SW: the two previous rows of M of every level live in
+// per-warp shared memory slots (row r in slot r & 1) instead of registers -- fewer registers, more warps per SM.
+template <int NT, bool BOX, bool PF, bool SW>
+__global__ void __launch_bounds__(256, SW ? 3 : 2)
 flow_strip_kernel(FlowArgs a, int SEG, int only_border)
 {
     constexpr int UW = 32 - 2 * NT;
     __shared__ unsigned int sH[RC_HIST_CELLS];
     __shared__ unsigned short sKeys[256];
     __shared__ int sNKeys;
-    const int w = a.w, h = a.h, j = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, pitch = a.pitch;
+    __shared__ float sWin[SW ? 8 : 1][SW ? NT : 1][2][5][SW ? 32 : 1];
+    const int w = a.w, h = a.h, j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, pitch = a.pitch;
     const bool do_hist = a.hist_delta != nullptr;
     if (do_hist) {
         for (int i = tid; i < RC_HIST_CELLS; i += 256) sH[i] = 0;
         if (tid == 0) sNKeys = 0;
         __syncthreads();
     }
-    const int sx0 = (blockIdx.x * 8 + wrp) * UW;
-    const int y0 = blockIdx.y * SEG;
+    const int sx0 = (blockIdx.y * 8 + wrp) * UW;             // grid = (pairs, strip groups, segments), pair fastest
+    const int y0 = blockIdx.z * SEG;
     // segments strictly inside the image are handled by flow_strip2_kernel when `only_border` is set
     const bool interior_seg = NT == 2 && y0 - 2 >= 0 && y0 + SEG + 2 <= h;
     if (only_border && interior_seg) return;
@@ -1119,31 +1124,32 @@ flow_strip_kernel(FlowArgs a, int SEG, int only_border)
         const float k0 = a.win.k[0], k1 = a.win.k[1], ps = a.win.post_scale;
         float2* outp = reinterpret_cast<float2*>(a.out(j));
 
-        float A[NT][5], B[NT][5];
+        float A[NT][5], B[NT][5];                            // register windows (unused when SW)
         int nfed[NT];
 #pragma unroll
         for (int it = 0; it < NT; it++) nfed[it] = 0;
         const int vbeg = max(y0 - NT, 0);
         const int vend = min(y0 + SEG - 1 + NT, h + NT - 1);
-        // level-0 gathers run one row ahead of the row being consumed
         UMIn pre;
-        auto prefetch0 = [&](int r) {
+        auto init_flow = [&](int r) {
             float2 fi = make_float2(0.f, 0.f);
             if (coarse) {
                 int csy; float cfy;
                 resize_coef(r, a.ch, a.sys, csy, cfy);
                 fi = upsample_flow_tab(coarse, a.cw, a.ch, csx, cfx, csy, cfy, a.fscale);
             }
-            um_load(pre, x, r, fi.x, fi.y, w, h, R0, R1, pitch);
+            return fi;
         };
-        prefetch0(min(vbeg, h - 1));
+        if (PF) { const int r = min(vbeg, h - 1); const float2 fi = init_flow(r); um_load(pre, x, r, fi.x, fi.y, w, h, R0, R1, pitch); }
 #pragma unroll 1
         for (int v = vbeg; v <= vend; v++) {
             bool produced = false;
             float2 f = make_float2(0.f, 0.f);
             float C0[5];
-            if (v < h) um_finish(pre, x, v, w, h, C0);
-            if (v + 1 < h && v + 1 <= vend) prefetch0(v + 1);
+            if (PF) {
+                if (v < h) um_finish(pre, x, v, w, h, C0);
+                if (v + 1 < h && v + 1 <= vend) { const float2 fi = init_flow(v + 1); um_load(pre, x, v + 1, fi.x, fi.y, w, h, R0, R1, pitch); }
+            }
 #pragma unroll
             for (int it = 0; it < NT; it++) {
                 const int r = v - it;
@@ -1151,8 +1157,13 @@ flow_strip_kernel(FlowArgs a, int SEG, int only_border)
                 bool have = false;
                 if (r >= 0 && r < h) {
                     if (it == 0) {
+                        if (PF) {
 #pragma unroll
-                        for (int c = 0; c < 5; c++) C[c] = C0[c];
+                            for (int c = 0; c < 5; c++) C[c] = C0[c];
+                        } else {
+                            const float2 fi = init_flow(r);
+                            update_matrices_core<false>(x, r, fi.x, fi.y, w, h, R0, R1, pitch, C);
+                        }
                         have = true;
                     } else if (produced) {
                         if (need_fix) { f.x = __shfl_sync(0xffffffffu, f.x, src_lane); f.y = __shfl_sync(0xffffffffu, f.y, src_lane); }
@@ -1161,14 +1172,17 @@ flow_strip_kernel(FlowArgs a, int SEG, int only_border)
                     }
                 } else if (r == h && nfed[it] > 0) {
 #pragma unroll
-                    for (int c = 0; c < 5; c++) C[c] = B[it][c];
+                    for (int c = 0; c < 5; c++) C[c] = SW ? sWin[wrp][it][(r - 1) & 1][c][lane] : B[it][c];
                     have = true;
                 }
                 produced = false;
                 if (!have) continue;
                 if (nfed[it] == 0) {
 #pragma unroll
-                    for (int c = 0; c < 5; c++) { B[it][c] = C[c]; A[it][c] = C[c]; }
+                    for (int c = 0; c < 5; c++) {
+                        if (SW) { sWin[wrp][it][0][c][lane] = C[c]; sWin[wrp][it][1][c][lane] = C[c]; }
+                        else { B[it][c] = C[c]; A[it][c] = C[c]; }
+                    }
                     nfed[it] = (r == 0) ? 2 : 1;
                     continue;
                 }
@@ -1176,7 +1190,9 @@ flow_strip_kernel(FlowArgs a, int SEG, int only_border)
                     float sv[5];
 #pragma unroll
                     for (int c = 0; c < 5; c++) {
-                        const float vs = BOX ? B[it][c] + (A[it][c] + C[c]) : fmaf(A[it][c] + C[c], k1, B[it][c] * k0);
+                        const float ra = SW ? sWin[wrp][it][r & 1][c][lane] : A[it][c];          // row r-2
+                        const float rb = SW ? sWin[wrp][it][(r - 1) & 1][c][lane] : B[it][c];    // row r-1
+                        const float vs = BOX ? rb + (ra + C[c]) : fmaf(ra + C[c], k1, rb * k0);
                         const float lft = __shfl_up_sync(0xffffffffu, vs, 1), rgt = __shfl_down_sync(0xffffffffu, vs, 1);
                         sv[c] = (BOX ? vs + (lft + rgt) : fmaf(lft + rgt, k1, vs * k0)) * ps;
                     }
@@ -1184,7 +1200,10 @@ flow_strip_kernel(FlowArgs a, int SEG, int only_border)
                     produced = true;
                 }
 #pragma unroll
-                for (int c = 0; c < 5; c++) { A[it][c] = B[it][c]; B[it][c] = C[c]; }
+                for (int c = 0; c < 5; c++) {
+                    if (SW) sWin[wrp][it][r & 1][c][lane] = C[c];
+                    else { A[it][c] = B[it][c]; B[it][c] = C[c]; }
+                }
                 nfed[it]++;
             }
             const int yo = v - NT;
@@ -1232,8 +1251,8 @@ flow_strip2_kernel(FlowArgs a, int SEG)
     __shared__ unsigned int sH[RC_HIST_CELLS];
     __shared__ unsigned short sKeys[256];
     __shared__ int sNKeys;
-    const int w = a.w, h = a.h, j = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, pitch = a.pitch;
-    const int y0 = blockIdx.y * SEG;
+    const int w = a.w, h = a.h, j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, pitch = a.pitch;
+    const int y0 = blockIdx.z * SEG;
     if (!(y0 - 2 >= 0 && y0 + SEG + 2 <= h)) return;            // border segment: flow_strip_kernel's job
     const bool do_hist = a.hist_delta != nullptr;
     if (do_hist) {
@@ -1241,7 +1260,7 @@ flow_strip2_kernel(FlowArgs a, int SEG)
         if (tid == 0) sNKeys = 0;
         __syncthreads();
     }
-    const int sx0 = (blockIdx.x * 8 + wrp) * UW;
+    const int sx0 = (blockIdx.y * 8 + wrp) * UW;
     if (sx0 < w) {
         const int xv = sx0 - NT + lane;
         const int x = clampi(xv, 0, w - 1);
@@ -1505,35 +1524,50 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         a.win = c->win;
         const double npx = (double)L.w * L.h * nb;
         if (fused_ok) {
-            dim3 g((L.w + 31) / 32, (L.h + 31) / 32, nb);
+            dim3 g(nb, (L.w + 31) / 32, (L.h + 31) / 32);
             KScope ks(c, K_FLOW_LAYER, (a.coarse ? 50.0 : 48.0) * npx);
-            static const int use_strip = getenv("RC_FLOW_STRIP") ? atoi(getenv("RC_FLOW_STRIP")) : 0;   // A/B switch
-            if (use_strip == 2 && T == 2) {
+            // which formulation of the fused layer runs (DESIGN.md section 7 compares them; all pass the parity tests):
+            //   RC_FLOW_KERNEL=strip (default)  warp strips, M rows in per-warp shared memory      -> use_strip 3
+            //                  tile             32x32 tiles, M in shared memory, block barriers      -> 0
+            //                  strip_reg        warp strips, M rows + prefetched gathers in registers -> 1
+            //                  strip_pipe       strip_reg + software pipelining of both gathers       -> 2
+            static const int use_strip = [] {
+                const char* e = getenv("RC_FLOW_KERNEL");
+                if (!e) return 3;
+                if (!strcmp(e, "tile")) return 0;
+                if (!strcmp(e, "strip_reg")) return 1;
+                if (!strcmp(e, "strip_pipe")) return 2;
+                return 3;
+            }();
+            // the strip kernels need many independent warps: on small launches the tile kernel is faster
+            static const double strip_min_px = getenv("RC_STRIP_MINPX") ? atof(getenv("RC_STRIP_MINPX")) : 16e6;
+            const int use_strip_here = npx >= strip_min_px ? use_strip : 0;
+            if (use_strip_here == 2 && T == 2) {
                 const int SEG = L.h >= 512 ? 64 : 32;
                 const int UW = 32 - 2 * T;
-                dim3 gs(((L.w + UW - 1) / UW + 7) / 8, (L.h + SEG - 1) / SEG, nb);
+                dim3 gs(nb, ((L.w + UW - 1) / UW + 7) / 8, (L.h + SEG - 1) / SEG);
                 if (!c->win.gaussian) {
                     flow_strip2_kernel<true><<<gs, 256, 0, c->stream>>>(a, SEG);
-                    flow_strip_kernel<2, true><<<gs, 256, 0, c->stream>>>(a, SEG, 1);
+                    flow_strip_kernel<2, true, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 1);
                 } else {
                     flow_strip2_kernel<false><<<gs, 256, 0, c->stream>>>(a, SEG);
-                    flow_strip_kernel<2, false><<<gs, 256, 0, c->stream>>>(a, SEG, 1);
+                    flow_strip_kernel<2, false, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 1);
                 }
                 c->launches += 1;
                 continue;
             }
-            if (use_strip) {
+            if (use_strip_here) {
                 const int SEG = L.h >= 512 ? 64 : 32;
                 const int UW = 32 - 2 * T;
-                dim3 gs(((L.w + UW - 1) / UW + 7) / 8, (L.h + SEG - 1) / SEG, nb);
+                dim3 gs(nb, ((L.w + UW - 1) / UW + 7) / 8, (L.h + SEG - 1) / SEG);
                 if (!c->win.gaussian) {
-                    if (T == 1) flow_strip_kernel<1, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0);
-                    else if (T == 2) flow_strip_kernel<2, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0);
-                    else flow_strip_kernel<3, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0);
+                    if (T == 1) do { if (use_strip_here == 3) flow_strip_kernel<1, true, false, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else if (use_strip_here == 4) flow_strip_kernel<1, true, true, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else flow_strip_kernel<1, true, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0); } while (0);
+                    else if (T == 2) do { if (use_strip_here == 3) flow_strip_kernel<2, true, false, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else if (use_strip_here == 4) flow_strip_kernel<2, true, true, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else flow_strip_kernel<2, true, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0); } while (0);
+                    else do { if (use_strip_here == 3) flow_strip_kernel<3, true, false, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else if (use_strip_here == 4) flow_strip_kernel<3, true, true, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else flow_strip_kernel<3, true, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0); } while (0);
                 } else {
-                    if (T == 1) flow_strip_kernel<1, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0);
-                    else if (T == 2) flow_strip_kernel<2, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0);
-                    else flow_strip_kernel<3, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0);
+                    if (T == 1) do { if (use_strip_here == 3) flow_strip_kernel<1, false, false, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else if (use_strip_here == 4) flow_strip_kernel<1, false, true, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else flow_strip_kernel<1, false, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0); } while (0);
+                    else if (T == 2) do { if (use_strip_here == 3) flow_strip_kernel<2, false, false, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else if (use_strip_here == 4) flow_strip_kernel<2, false, true, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else flow_strip_kernel<2, false, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0); } while (0);
+                    else do { if (use_strip_here == 3) flow_strip_kernel<3, false, false, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else if (use_strip_here == 4) flow_strip_kernel<3, false, true, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else flow_strip_kernel<3, false, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0); } while (0);
                 }
                 continue;
             }
@@ -1565,7 +1599,7 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
                 configured[c->device & 63] = tsm;
             }
         }
-        dim3 gt((L.w + 63) / 64, (L.h + 15) / 16, nb);
+        dim3 gt(nb, (L.w + 63) / 64, (L.h + 15) / 16);
         const bool box = !c->win.gaussian;
         const bool spec = tiled && (m == 2 || m == 5 || m == 10);
         bool hist_fused = false;
