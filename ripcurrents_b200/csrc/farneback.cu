@@ -1091,7 +1091,7 @@ flow_layer_kernel(FlowArgs a)
 // PF: level-0 gathers prefetched one row ahead (registers).  SW: the two previous rows of M of every level live in
 // per-warp shared memory slots (row r in slot r & 1) instead of registers -- fewer registers, more warps per SM.
 template <int NT, bool BOX, bool PF, bool SW>
-__global__ void __launch_bounds__(256, SW ? 3 : 2)
+__global__ void __launch_bounds__(256, SW ? 4 : 2)
 flow_strip_kernel(FlowArgs a, int SEG, int only_border)
 {
     constexpr int UW = 32 - 2 * NT;
@@ -1557,7 +1557,10 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
                 continue;
             }
             if (use_strip_here) {
-                const int SEG = L.h >= 512 ? 64 : 32;
+                static const int seg_env = getenv("RC_STRIP_SEG") ? atoi(getenv("RC_STRIP_SEG")) : 0;
+                // ~48-row segments, evened out over the layer height (2T halo rows are recomputed per segment)
+                const int nseg = (L.h + 47) / 48;
+                const int SEG = seg_env > 0 ? seg_env : (L.h + nseg - 1) / nseg;
                 const int UW = 32 - 2 * T;
                 dim3 gs(nb, ((L.w + UW - 1) / UW + 7) / 8, (L.h + SEG - 1) / SEG);
                 if (!c->win.gaussian) {
