@@ -235,6 +235,54 @@ pyr_half_kernel(const uint8_t* __restrict__ img, size_t step, size_t fstride, in
     *reinterpret_cast<float2*>(out + (size_t)Y * pitch + X) = make_float2(r[0], r[1]);
 }
 
+// Exact 4:1 layer with the 9-tap presmooth (pyr_scale 0.5, layer 2: sigma 1.5): the resize samples source columns
+// 4X+1, 4X+2 (rows 4Y+1, 4Y+2) with weight 1/2, so a destination pixel is a fixed 10x10 source window.  One thread per
+// destination pixel; interior pixels read three aligned 32-bit words per row, border pixels gather bytes with
+// REFLECT_101.  Arithmetic order identical to pyr_tile_kernel.
+__global__ void __launch_bounds__(256)
+pyr_quarter_kernel(const uint8_t* __restrict__ img, size_t step, size_t fstride, int W, int H, int dw, int dh, SmoothCoef sc,
+                   float* __restrict__ out, int pitch, size_t ostride)
+{
+    const int X = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (X >= dw || Y >= dh) return;
+    img += (size_t)blockIdx.z * fstride;
+    out += (size_t)blockIdx.z * ostride;
+    const int cx = 4 * X - 3, cy = 4 * Y - 3;                      // window origin: columns cx..cx+9, rows cy..cy+9
+    const bool inner = cx >= 1 && cx + 11 <= W && cy >= 0 && cy + 9 < H;
+    float k[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) k[i] = sc.k[i];
+    float h0[10], h1[10];                                          // H-blurred values at columns 4X+1 / 4X+2, per window row
+#pragma unroll
+    for (int rr = 0; rr < 10; rr++) {
+        float v[10];
+        if (inner) {
+            const unsigned int* p = reinterpret_cast<const unsigned int*>(img + (size_t)(cy + rr) * step + (cx - 1));
+            const unsigned int w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);    // bytes cx-1 .. cx+10
+            v[0] = (float)((w0 >> 8) & 0xff); v[1] = (float)((w0 >> 16) & 0xff); v[2] = (float)(w0 >> 24);
+            v[3] = (float)(w1 & 0xff); v[4] = (float)((w1 >> 8) & 0xff); v[5] = (float)((w1 >> 16) & 0xff); v[6] = (float)(w1 >> 24);
+            v[7] = (float)(w2 & 0xff); v[8] = (float)((w2 >> 8) & 0xff); v[9] = (float)((w2 >> 16) & 0xff);
+        } else {
+            const uint8_t* row = img + (size_t)reflect101(cy + rr, H) * step;
+#pragma unroll
+            for (int i = 0; i < 10; i++) v[i] = (float)row[reflect101(cx + i, W)];
+        }
+        float s0 = __fmul_rn(k[0], v[0]), s1 = __fmul_rn(k[0], v[1]);
+#pragma unroll
+        for (int i = 1; i < 9; i++) { s0 = __fadd_rn(s0, __fmul_rn(k[i], v[i])); s1 = __fadd_rn(s1, __fmul_rn(k[i], v[i + 1])); }
+        h0[rr] = s0; h1[rr] = s1;
+    }
+    float b00 = __fmul_rn(k[0], h0[0]), b01 = __fmul_rn(k[0], h1[0]), b10 = __fmul_rn(k[0], h0[1]), b11 = __fmul_rn(k[0], h1[1]);
+#pragma unroll
+    for (int j = 1; j < 9; j++) {
+        b00 = __fadd_rn(b00, __fmul_rn(k[j], h0[j])); b01 = __fadd_rn(b01, __fmul_rn(k[j], h1[j]));
+        b10 = __fadd_rn(b10, __fmul_rn(k[j], h0[j + 1])); b11 = __fadd_rn(b11, __fmul_rn(k[j], h1[j + 1]));
+    }
+    const float top = __fadd_rn(__fmul_rn(b00, 0.5f), __fmul_rn(b01, 0.5f));
+    const float bot = __fadd_rn(__fmul_rn(b10, 0.5f), __fmul_rn(b11, 0.5f));
+    out[(size_t)Y * pitch + X] = __fadd_rn(__fmul_rn(top, 0.5f), __fmul_rn(bot, 0.5f));
+}
+
 // Layer 0 (no resize; OpenCV's 3-tap [1/4 1/2 1/4] presmooth): each thread produces 4 adjacent pixels from three
 // 4-byte row loads + two edge bytes per row.  Same tap order and separately rounded products as the tile kernel.
 __global__ void __launch_bounds__(256)
@@ -1458,6 +1506,17 @@ void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fs
                 KScope ks(c, K_PYR_V, 4.0 * L.w * L.h * nb);
                 pyr_half_kernel<<<g, 256, 0, c->stream>>>(d_frames, step, fstride, W, H, L.w, L.h, L.smooth.k[0],
                                                          L.smooth.k[1], L.smooth.k[2], L.I, L.pitch, (size_t)L.pitch * L.h);
+            }
+            launch_polyexp(c, L, nb, first_slot);
+            continue;
+        }
+        if (a.two && L.smooth.ksize == 9 && W == 4 * L.w && H == 4 * L.h && W >= 16 && H >= 16 && step % 4 == 0 &&
+            fstride % 4 == 0 && (reinterpret_cast<size_t>(d_frames) & 3) == 0) {
+            dim3 g((L.w + 31) / 32, (L.h + 7) / 8, nb);
+            {
+                KScope ks(c, K_PYR_V, 4.0 * L.w * L.h * nb);
+                pyr_quarter_kernel<<<g, 256, 0, c->stream>>>(d_frames, step, fstride, W, H, L.w, L.h, L.smooth, L.I, L.pitch,
+                                                            (size_t)L.pitch * L.h);
             }
             launch_polyexp(c, L, nb, first_slot);
             continue;
