@@ -564,68 +564,6 @@ __device__ __forceinline__ void update_matrices_core(int x, int y, float dx, flo
     m[4] = fadd<S>(fmul<S>(r6, r2), fmul<S>(r5, r3));
 }
 
-// Fast-path split of updateMatrices into a load half and a math half: the strip kernel issues the gathers of the
-// next row before it consumes the current one.
-struct UMIn {
-    float4 r0, t00, t01, t10, t11;
-    float r0_4, u00, u01, u10, u11;
-    float fx, fy, dx, dy;
-    bool inside;
-};
-
-__device__ __forceinline__ void um_load(UMIn& u, int x, int y, float dx, float dy, int w, int h, const RView& R0,
-                                        const RView& R1, int pitch)
-{
-    const int p = y * pitch + x;
-    const float fx = (float)x + dx, fy = (float)y + dy;
-    const float flx = floorf(fx), fly = floorf(fy);
-    const int x1 = (int)flx, y1 = (int)fly;
-    u.fx = fx - flx; u.fy = fy - fly; u.dx = dx; u.dy = dy;
-    u.r0 = __ldg(R0.A + p);
-    u.r0_4 = __ldg(R0.B + p);
-    u.inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
-    // out-of-range gathers are redirected to a valid address near the pixel itself; their values are not used
-    const int q = u.inside ? y1 * pitch + x1 : (y < h - 1 ? p : p - pitch) - (x < w - 1 ? 0 : 1);
-    u.t00 = __ldg(R1.A + q); u.t01 = __ldg(R1.A + q + 1);
-    u.t10 = __ldg(R1.A + q + pitch); u.t11 = __ldg(R1.A + q + pitch + 1);
-    u.u00 = __ldg(R1.B + q); u.u01 = __ldg(R1.B + q + 1);
-    u.u10 = __ldg(R1.B + q + pitch); u.u11 = __ldg(R1.B + q + pitch + 1);
-}
-
-__device__ __forceinline__ void um_finish(const UMIn& u, int x, int y, int w, int h, float m[5])
-{
-    float r2, r3, r4, r5, r6;
-    if (u.inside) {
-        const float gx = 1.f - u.fx, gy = 1.f - u.fy;
-        const float a00 = gx * gy, a01 = u.fx * gy, a10 = gx * u.fy, a11 = u.fx * u.fy;
-#define RC_BILERP(c00, c01, c10, c11) (((a00 * (c00) + a01 * (c01)) + a10 * (c10)) + a11 * (c11))
-        r2 = RC_BILERP(u.t00.x, u.t01.x, u.t10.x, u.t11.x);
-        r3 = RC_BILERP(u.t00.y, u.t01.y, u.t10.y, u.t11.y);
-        r4 = (u.r0.z + RC_BILERP(u.t00.z, u.t01.z, u.t10.z, u.t11.z)) * 0.5f;
-        r5 = (u.r0.w + RC_BILERP(u.t00.w, u.t01.w, u.t10.w, u.t11.w)) * 0.5f;
-        r6 = (u.r0_4 + RC_BILERP(u.u00, u.u01, u.u10, u.u11)) * 0.25f;
-#undef RC_BILERP
-    } else {
-        r2 = r3 = 0.f;
-        r4 = u.r0.z; r5 = u.r0.w; r6 = u.r0_4 * 0.5f;
-    }
-    r2 = (u.r0.x - r2) * 0.5f;
-    r3 = (u.r0.y - r3) * 0.5f;
-    r2 = r2 + (r4 * u.dy + r6 * u.dx);
-    r3 = r3 + (r6 * u.dy + r5 * u.dx);
-    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
-        auto bw = [](int d) { return d >= 5 ? 1.f : (d < 2 ? 0.14f : 0.4472f); };
-        float scale = __fmul_rn(__fmul_rn(__fmul_rn(bw(x), bw(w - x - 1)), bw(y)), bw(h - y - 1));
-        r2 = __fmul_rn(r2, scale); r3 = __fmul_rn(r3, scale); r4 = __fmul_rn(r4, scale);
-        r5 = __fmul_rn(r5, scale); r6 = __fmul_rn(r6, scale);
-    }
-    m[0] = r4 * r4 + r6 * r6;
-    m[1] = (r4 + r5) * r6;
-    m[2] = r5 * r5 + r6 * r6;
-    m[3] = r4 * r2 + r6 * r3;
-    m[4] = r6 * r2 + r5 * r3;
-}
-
 // Flow initialisation of Appendix A.4 at pixel (x, y) of a w x h layer from the coarser layer's flow.
 template <bool S>
 __device__ __forceinline__ float2 upsample_flow(const float* __restrict__ coarse, int cw, int ch, int x, int y,
@@ -1136,17 +1074,18 @@ flow_layer_kernel(FlowArgs a)
 // are evaluated at clamped pixels, deeper levels duplicate their first/last real row and copy the flow of the
 // clamped column before updateMatrices, which reproduces M at the clamped pixel exactly.
 // ---------------------------------------------------------------------------------------------------
-// PF: level-0 gathers prefetched one row ahead (registers).  SW: the two previous rows of M of every level live in
-// per-warp shared memory slots (row r in slot r & 1) instead of registers -- fewer registers, more warps per SM.
-template <int NT, bool BOX, bool PF, bool SW>
-__global__ void __launch_bounds__(256, SW ? 4 : 2)
-flow_strip_kernel(FlowArgs a, int SEG, int only_border)
+// The two previous rows of M of every level live in per-warp shared memory slots (row r in slot r & 1): 64 registers,
+// 32 warps per SM.  (Variants that kept them in registers and prefetched the gathers were measured and dropped: fewer
+// instructions but half the occupancy)
+template <int NT, bool BOX>
+__global__ void __launch_bounds__(256, 4)
+flow_strip_kernel(FlowArgs a, int SEG)
 {
     constexpr int UW = 32 - 2 * NT;
     __shared__ unsigned int sH[RC_HIST_CELLS];
     __shared__ unsigned short sKeys[256];
     __shared__ int sNKeys;
-    __shared__ float sWin[SW ? 8 : 1][SW ? NT : 1][2][5][SW ? 32 : 1];
+    __shared__ float sWin[8][NT][2][5][32];
     const int w = a.w, h = a.h, j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, pitch = a.pitch;
     const bool do_hist = a.hist_delta != nullptr;
     if (do_hist) {
@@ -1156,9 +1095,6 @@ flow_strip_kernel(FlowArgs a, int SEG, int only_border)
     }
     const int sx0 = (blockIdx.y * 8 + wrp) * UW;             // grid = (pairs, strip groups, segments), pair fastest
     const int y0 = blockIdx.z * SEG;
-    // segments strictly inside the image are handled by flow_strip2_kernel when `only_border` is set
-    const bool interior_seg = NT == 2 && y0 - 2 >= 0 && y0 + SEG + 2 <= h;
-    if (only_border && interior_seg) return;
     if (sx0 < w) {
         const int xv = sx0 - NT + lane;
         const int x = clampi(xv, 0, w - 1);
@@ -1172,13 +1108,11 @@ flow_strip_kernel(FlowArgs a, int SEG, int only_border)
         const float k0 = a.win.k[0], k1 = a.win.k[1], ps = a.win.post_scale;
         float2* outp = reinterpret_cast<float2*>(a.out(j));
 
-        float A[NT][5], B[NT][5];                            // register windows (unused when SW)
         int nfed[NT];
 #pragma unroll
         for (int it = 0; it < NT; it++) nfed[it] = 0;
         const int vbeg = max(y0 - NT, 0);
         const int vend = min(y0 + SEG - 1 + NT, h + NT - 1);
-        UMIn pre;
         auto init_flow = [&](int r) {
             float2 fi = make_float2(0.f, 0.f);
             if (coarse) {
@@ -1188,16 +1122,10 @@ flow_strip_kernel(FlowArgs a, int SEG, int only_border)
             }
             return fi;
         };
-        if (PF) { const int r = min(vbeg, h - 1); const float2 fi = init_flow(r); um_load(pre, x, r, fi.x, fi.y, w, h, R0, R1, pitch); }
 #pragma unroll 1
         for (int v = vbeg; v <= vend; v++) {
             bool produced = false;
             float2 f = make_float2(0.f, 0.f);
-            float C0[5];
-            if (PF) {
-                if (v < h) um_finish(pre, x, v, w, h, C0);
-                if (v + 1 < h && v + 1 <= vend) { const float2 fi = init_flow(v + 1); um_load(pre, x, v + 1, fi.x, fi.y, w, h, R0, R1, pitch); }
-            }
 #pragma unroll
             for (int it = 0; it < NT; it++) {
                 const int r = v - it;
@@ -1205,13 +1133,8 @@ flow_strip_kernel(FlowArgs a, int SEG, int only_border)
                 bool have = false;
                 if (r >= 0 && r < h) {
                     if (it == 0) {
-                        if (PF) {
-#pragma unroll
-                            for (int c = 0; c < 5; c++) C[c] = C0[c];
-                        } else {
-                            const float2 fi = init_flow(r);
-                            update_matrices_core<false>(x, r, fi.x, fi.y, w, h, R0, R1, pitch, C);
-                        }
+                        const float2 fi = init_flow(r);
+                        update_matrices_core<false>(x, r, fi.x, fi.y, w, h, R0, R1, pitch, C);
                         have = true;
                     } else if (produced) {
                         if (need_fix) { f.x = __shfl_sync(0xffffffffu, f.x, src_lane); f.y = __shfl_sync(0xffffffffu, f.y, src_lane); }
@@ -1220,17 +1143,14 @@ flow_strip_kernel(FlowArgs a, int SEG, int only_border)
                     }
                 } else if (r == h && nfed[it] > 0) {
 #pragma unroll
-                    for (int c = 0; c < 5; c++) C[c] = SW ? sWin[wrp][it][(r - 1) & 1][c][lane] : B[it][c];
+                    for (int c = 0; c < 5; c++) C[c] = sWin[wrp][it][(r - 1) & 1][c][lane];
                     have = true;
                 }
                 produced = false;
                 if (!have) continue;
                 if (nfed[it] == 0) {
 #pragma unroll
-                    for (int c = 0; c < 5; c++) {
-                        if (SW) { sWin[wrp][it][0][c][lane] = C[c]; sWin[wrp][it][1][c][lane] = C[c]; }
-                        else { B[it][c] = C[c]; A[it][c] = C[c]; }
-                    }
+                    for (int c = 0; c < 5; c++) { sWin[wrp][it][0][c][lane] = C[c]; sWin[wrp][it][1][c][lane] = C[c]; }
                     nfed[it] = (r == 0) ? 2 : 1;
                     continue;
                 }
@@ -1238,8 +1158,8 @@ flow_strip_kernel(FlowArgs a, int SEG, int only_border)
                     float sv[5];
 #pragma unroll
                     for (int c = 0; c < 5; c++) {
-                        const float ra = SW ? sWin[wrp][it][r & 1][c][lane] : A[it][c];          // row r-2
-                        const float rb = SW ? sWin[wrp][it][(r - 1) & 1][c][lane] : B[it][c];    // row r-1
+                        const float ra = sWin[wrp][it][r & 1][c][lane];          // row r-2
+                        const float rb = sWin[wrp][it][(r - 1) & 1][c][lane];    // row r-1
                         const float vs = BOX ? rb + (ra + C[c]) : fmaf(ra + C[c], k1, rb * k0);
                         const float lft = __shfl_up_sync(0xffffffffu, vs, 1), rgt = __shfl_down_sync(0xffffffffu, vs, 1);
                         sv[c] = (BOX ? vs + (lft + rgt) : fmaf(lft + rgt, k1, vs * k0)) * ps;
@@ -1248,10 +1168,7 @@ flow_strip_kernel(FlowArgs a, int SEG, int only_border)
                     produced = true;
                 }
 #pragma unroll
-                for (int c = 0; c < 5; c++) {
-                    if (SW) sWin[wrp][it][r & 1][c][lane] = C[c];
-                    else { A[it][c] = B[it][c]; B[it][c] = C[c]; }
-                }
+                for (int c = 0; c < 5; c++) sWin[wrp][it][r & 1][c][lane] = C[c];
                 nfed[it]++;
             }
             const int yo = v - NT;
@@ -1260,115 +1177,6 @@ flow_strip_kernel(FlowArgs a, int SEG, int only_border)
                 if (col_out) outp[yo * w + xv] = f;
                 if (do_hist) {
                     const int key = col_out ? hist_key_fast(f.x, f.y) : -1;
-                    const unsigned peers = __match_any_sync(0xffffffffu, key);
-                    if (key >= 0 && (int)(__ffs(peers) - 1) == lane) {
-                        if (atomicAdd(&sH[key], __popc(peers)) == 0) {
-                            const int slot = atomicAdd(&sNKeys, 1);
-                            if (slot < 256) sKeys[slot] = (unsigned short)key;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    if (do_hist) {
-        __syncthreads();
-        unsigned int* dst = a.hist_delta + (size_t)j * RC_HIST_CELLS;
-        const int nk = sNKeys;
-        if (nk <= 256) {
-            if (tid < nk) { const int k = sKeys[tid]; atomicAdd(&dst[k], sH[k]); }
-        } else {
-            for (int i = tid; i < RC_HIST_CELLS; i += 256)
-                if (sH[i]) atomicAdd(&dst[i], sH[i]);
-        }
-    }
-}
-
-// Software-pipelined strip kernel for the reference default (2 iterations), segments strictly inside the image:
-// the gathers of BOTH updateMatrices evaluations are issued one row before they are consumed, so no load latency
-// sits on the per-row dependency chain (M0[v] -> flow1[v-1] -> M1[v-1] -> flow2[v-2]).  Row v of the loop:
-//   finish M0[v] (gathers issued at v-1), issue the gathers of M0[v+1];
-//   flow1[v-1] from M0[v-2..v]; finish M1[v-2] (gathers issued at v-1), issue those of M1[v-1] with flow1[v-1];
-//   flow2[v-3] from M1[v-4..v-2] -> output row v-3.
-// Segments touching the top / bottom border run in flow_strip_kernel (replicate handling), launched alongside.
-template <bool BOX>
-__global__ void __launch_bounds__(256)
-flow_strip2_kernel(FlowArgs a, int SEG)
-{
-    constexpr int NT = 2, UW = 32 - 2 * NT;
-    __shared__ unsigned int sH[RC_HIST_CELLS];
-    __shared__ unsigned short sKeys[256];
-    __shared__ int sNKeys;
-    const int w = a.w, h = a.h, j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, pitch = a.pitch;
-    const int y0 = blockIdx.z * SEG;
-    if (!(y0 - 2 >= 0 && y0 + SEG + 2 <= h)) return;            // border segment: flow_strip_kernel's job
-    const bool do_hist = a.hist_delta != nullptr;
-    if (do_hist) {
-        for (int i = tid; i < RC_HIST_CELLS; i += 256) sH[i] = 0;
-        if (tid == 0) sNKeys = 0;
-        __syncthreads();
-    }
-    const int sx0 = (blockIdx.y * 8 + wrp) * UW;
-    if (sx0 < w) {
-        const int xv = sx0 - NT + lane;
-        const int x = clampi(xv, 0, w - 1);
-        const bool col_out = lane >= NT && lane < 32 - NT && xv < w;
-        const bool need_fix = (sx0 - NT < 0) || (sx0 - NT + 31 >= w);
-        const int src_lane = x - (sx0 - NT);
-        const RView R0 = rview(a.R0(j), a.plane), R1 = rview(a.R1(j), a.plane);
-        const float2* coarse = a.coarse ? reinterpret_cast<const float2*>(a.coarse + (size_t)j * a.coarse_stride) : nullptr;
-        int csx = 0; float cfx = 0.f;
-        if (coarse) resize_coef(x, a.cw, a.sxs, csx, cfx);
-        const float k0 = a.win.k[0], k1 = a.win.k[1], ps = a.win.post_scale;
-        float2* outp = reinterpret_cast<float2*>(a.out(j));
-
-        UMIn p0, p1;                      // gathers in flight for level 0 (row v+1) and level 1 (row v-1)
-        auto issue0 = [&](int r) {
-            float2 fi = make_float2(0.f, 0.f);
-            if (coarse) {
-                int csy; float cfy;
-                resize_coef(r, a.ch, a.sys, csy, cfy);
-                fi = upsample_flow_tab(coarse, a.cw, a.ch, csx, cfx, csy, cfy, a.fscale);
-            }
-            um_load(p0, x, r, fi.x, fi.y, w, h, R0, R1, pitch);
-        };
-        float A0[5], B0[5], A1[5], B1[5];
-#pragma unroll
-        for (int c = 0; c < 5; c++) { A0[c] = B0[c] = A1[c] = B1[c] = 0.f; }
-        const int v0 = y0 - 2, vend = y0 + SEG + 2;               // rows v0 .. vend inclusive (vend <= h - ... + 0)
-        issue0(v0);
-        um_load(p1, x, v0, 0.f, 0.f, w, h, R0, R1, pitch);         // dummy, keeps the pipeline uniform (result unused)
-#pragma unroll 1
-        for (int v = v0; v <= vend; v++) {
-            float C0[5], C1[5];
-            um_finish(p0, x, v, w, h, C0);                         // M0[v]
-            if (v < vend) issue0(min(v + 1, h - 1));
-            um_finish(p1, x, max(v - 2, 0), w, h, C1);             // M1[v-2] (garbage during warm-up, never output)
-            float sv[5];
-#pragma unroll
-            for (int c = 0; c < 5; c++) {
-                const float vs = BOX ? B0[c] + (A0[c] + C0[c]) : fmaf(A0[c] + C0[c], k1, B0[c] * k0);
-                const float lft = __shfl_up_sync(0xffffffffu, vs, 1), rgt = __shfl_down_sync(0xffffffffu, vs, 1);
-                sv[c] = (BOX ? vs + (lft + rgt) : fmaf(lft + rgt, k1, vs * k0)) * ps;
-                A0[c] = B0[c]; B0[c] = C0[c];
-            }
-            float2 f1 = solve_fast(sv[0], sv[1], sv[2], sv[3], sv[4]);          // flow1[v-1]
-            if (need_fix) { f1.x = __shfl_sync(0xffffffffu, f1.x, src_lane); f1.y = __shfl_sync(0xffffffffu, f1.y, src_lane); }
-            if (!(fabsf(f1.x) < 1e18f) || !(fabsf(f1.y) < 1e18f)) f1 = make_float2(0.f, 0.f);   // warm-up rows / edge lanes only
-            um_load(p1, x, max(v - 1, 0), f1.x, f1.y, w, h, R0, R1, pitch);     // gathers of M1[v-1]
-#pragma unroll
-            for (int c = 0; c < 5; c++) {
-                const float vs = BOX ? B1[c] + (A1[c] + C1[c]) : fmaf(A1[c] + C1[c], k1, B1[c] * k0);
-                const float lft = __shfl_up_sync(0xffffffffu, vs, 1), rgt = __shfl_down_sync(0xffffffffu, vs, 1);
-                sv[c] = (BOX ? vs + (lft + rgt) : fmaf(lft + rgt, k1, vs * k0)) * ps;
-                A1[c] = B1[c]; B1[c] = C1[c];
-            }
-            const float2 f2 = solve_fast(sv[0], sv[1], sv[2], sv[3], sv[4]);    // flow2[v-3]
-            const int yo = v - 3;
-            if (yo >= y0 && yo < y0 + SEG) {                                     // warp-uniform
-                if (col_out) outp[yo * w + xv] = f2;
-                if (do_hist) {
-                    const int key = col_out ? hist_key_fast(f2.x, f2.y) : -1;
                     const unsigned peers = __match_any_sync(0xffffffffu, key);
                     if (key >= 0 && (int)(__ffs(peers) - 1) == lane) {
                         if (atomicAdd(&sH[key], __popc(peers)) == 0) {
@@ -1585,51 +1393,29 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         if (fused_ok) {
             dim3 g(nb, (L.w + 31) / 32, (L.h + 31) / 32);
             KScope ks(c, K_FLOW_LAYER, (a.coarse ? 50.0 : 48.0) * npx);
-            // which formulation of the fused layer runs (DESIGN.md section 7 compares them; all pass the parity tests):
-            //   RC_FLOW_KERNEL=strip (default)  warp strips, M rows in per-warp shared memory      -> use_strip 3
-            //                  tile             32x32 tiles, M in shared memory, block barriers      -> 0
-            //                  strip_reg        warp strips, M rows + prefetched gathers in registers -> 1
-            //                  strip_pipe       strip_reg + software pipelining of both gathers       -> 2
-            static const int use_strip = [] {
+            // Formulation of the fused layer (both pass the same parity tests): warp strips with M rows in
+            // per-warp shared memory on big launches, 32x32 shared-memory tiles otherwise.  RC_FLOW_KERNEL=tile|strip forces
+            // one of them, RC_STRIP_MINPX moves the switch-over point (pixel*pairs per launch).
+            static const int force = [] {
                 const char* e = getenv("RC_FLOW_KERNEL");
-                if (!e) return 3;
-                if (!strcmp(e, "tile")) return 0;
-                if (!strcmp(e, "strip_reg")) return 1;
-                if (!strcmp(e, "strip_pipe")) return 2;
-                return 3;
+                return !e ? 0 : (!strcmp(e, "tile") ? 1 : (!strcmp(e, "strip") ? 2 : 0));
             }();
-            // the strip kernels need many independent warps: on small launches the tile kernel is faster
             static const double strip_min_px = getenv("RC_STRIP_MINPX") ? atof(getenv("RC_STRIP_MINPX")) : 16e6;
-            const int use_strip_here = npx >= strip_min_px ? use_strip : 0;
-            if (use_strip_here == 2 && T == 2) {
-                const int SEG = L.h >= 512 ? 64 : 32;
-                const int UW = 32 - 2 * T;
-                dim3 gs(nb, ((L.w + UW - 1) / UW + 7) / 8, (L.h + SEG - 1) / SEG);
-                if (!c->win.gaussian) {
-                    flow_strip2_kernel<true><<<gs, 256, 0, c->stream>>>(a, SEG);
-                    flow_strip_kernel<2, true, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 1);
-                } else {
-                    flow_strip2_kernel<false><<<gs, 256, 0, c->stream>>>(a, SEG);
-                    flow_strip_kernel<2, false, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 1);
-                }
-                c->launches += 1;
-                continue;
-            }
-            if (use_strip_here) {
-                static const int seg_env = getenv("RC_STRIP_SEG") ? atoi(getenv("RC_STRIP_SEG")) : 0;
+            static const int seg_env = getenv("RC_STRIP_SEG") ? atoi(getenv("RC_STRIP_SEG")) : 0;
+            if (force == 2 || (force == 0 && npx >= strip_min_px)) {
                 // ~48-row segments, evened out over the layer height (2T halo rows are recomputed per segment)
                 const int nseg = (L.h + 47) / 48;
                 const int SEG = seg_env > 0 ? seg_env : (L.h + nseg - 1) / nseg;
                 const int UW = 32 - 2 * T;
                 dim3 gs(nb, ((L.w + UW - 1) / UW + 7) / 8, (L.h + SEG - 1) / SEG);
                 if (!c->win.gaussian) {
-                    if (T == 1) do { if (use_strip_here == 3) flow_strip_kernel<1, true, false, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else if (use_strip_here == 4) flow_strip_kernel<1, true, true, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else flow_strip_kernel<1, true, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0); } while (0);
-                    else if (T == 2) do { if (use_strip_here == 3) flow_strip_kernel<2, true, false, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else if (use_strip_here == 4) flow_strip_kernel<2, true, true, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else flow_strip_kernel<2, true, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0); } while (0);
-                    else do { if (use_strip_here == 3) flow_strip_kernel<3, true, false, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else if (use_strip_here == 4) flow_strip_kernel<3, true, true, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else flow_strip_kernel<3, true, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0); } while (0);
+                    if (T == 1) flow_strip_kernel<1, true><<<gs, 256, 0, c->stream>>>(a, SEG);
+                    else if (T == 2) flow_strip_kernel<2, true><<<gs, 256, 0, c->stream>>>(a, SEG);
+                    else flow_strip_kernel<3, true><<<gs, 256, 0, c->stream>>>(a, SEG);
                 } else {
-                    if (T == 1) do { if (use_strip_here == 3) flow_strip_kernel<1, false, false, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else if (use_strip_here == 4) flow_strip_kernel<1, false, true, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else flow_strip_kernel<1, false, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0); } while (0);
-                    else if (T == 2) do { if (use_strip_here == 3) flow_strip_kernel<2, false, false, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else if (use_strip_here == 4) flow_strip_kernel<2, false, true, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else flow_strip_kernel<2, false, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0); } while (0);
-                    else do { if (use_strip_here == 3) flow_strip_kernel<3, false, false, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else if (use_strip_here == 4) flow_strip_kernel<3, false, true, true><<<gs, 256, 0, c->stream>>>(a, SEG, 0); else flow_strip_kernel<3, false, true, false><<<gs, 256, 0, c->stream>>>(a, SEG, 0); } while (0);
+                    if (T == 1) flow_strip_kernel<1, false><<<gs, 256, 0, c->stream>>>(a, SEG);
+                    else if (T == 2) flow_strip_kernel<2, false><<<gs, 256, 0, c->stream>>>(a, SEG);
+                    else flow_strip_kernel<3, false><<<gs, 256, 0, c->stream>>>(a, SEG);
                 }
                 continue;
             }
