@@ -238,6 +238,39 @@ int rc_submit_frames_bgr(rc_ctx* ctx, const uint8_t* bgr_frames, size_t step, si
 int rc_mask_edges(rc_ctx* ctx, const uint8_t* masks, size_t mask_step, size_t mask_stride, int w, int h, int count,
                   uint8_t* edges, size_t edges_step, size_t edges_stride);
 
+/* ---- derived fields of the per-pixel particle state -----------------------------
+ * What ripcurrents.cpp:231-279 (== ripcurrents_module.cpp:13-59, called from main_old.cpp:373-386) computes after
+ * streamline_field() with split / magnitude / minMaxLoc / convertTo / applyColorMap(JET) / divide and the position
+ * scatter.  Bit-exact against cv2 4.13 (cv2.magnitude compared with cv2.setUseOptimized(False); the IPP-backed default
+ * differs from OpenCV's own definition by <= 2 ulp).  All arrays are dense (no row padding); every pointer may be a host
+ * or a device pointer; optional outputs may be NULL.  Calls with only device pointers and maxes == NULL are asynchronous
+ * on the context's stream. */
+#define RC_FIELDS_DIV_ZERO_IS_ZERO 1   /* cv::divide of OpenCV 3.x (the version the reference names): x / 0 -> 0;
+                                          default is OpenCV 4.x: IEEE inf / NaN */
+#define RC_FIELDS_KEEP_DENSITY 2       /* do not clear `density` first (module:44 takes the caller's Mat as it is;
+                                          ripcurrents.cpp:261 starts from Mat::zeros, the default) */
+/* One call for the whole block: field = streamlines_mat (w*h float2 displacements), dist = streamlines_distance.
+ *   streamfield  magnitude(field)                                                       (ripcurrents.cpp:232-233)
+ *   disp_bgr     JET(convertTo(streamfield, 255 / max))      "streamline displacement"  (:236-240, module:13-19)
+ *   motion_bgr   JET(convertTo(dist, 255 / max))             "streamline total motion"  (:243-247, module:23-28)
+ *   ratio_bgr    JET(convertTo(streamfield / dist, 255/max)) "displacement/motion ratio"(:250-256, module:34-40)
+ *   density      CV_32FC3, (1,1,1) where a particle ends up                             (:261-276, module:44-59)
+ *   maxes        {lenmax, distmax, ratiomax}; NaNs are ignored by the maxima (cv2 4.x returns a SIMD-lane dependent
+ *                value when NaNs are present), NaN only if every element is NaN. */
+int rc_particle_fields(rc_ctx* ctx, const float* field, const float* dist, int w, int h, int flags, float* streamfield,
+                       uint8_t* disp_bgr, uint8_t* motion_bgr, uint8_t* ratio_bgr, float* density, double* maxes);
+/* The pieces, as the module factors them.  streamline_displacement / streamline_total_motion (module:13-29):
+ * minMaxLoc -> convertTo(CV_8UC1, 255/max) -> applyColorMap(JET) of n floats; gray (before the colour map) and bgr
+ * are optional. */
+int rc_normalize_jet(rc_ctx* ctx, const float* src, size_t n, uint8_t* gray, uint8_t* bgr, double* maxval);
+/* streamline_ratio (module:34-40): divide(a, b) then the same normalisation; `ratio` (optional) receives a / b. */
+int rc_ratio_jet(rc_ctx* ctx, const float* a, const float* b, size_t n, int flags, float* ratio, uint8_t* gray,
+                 uint8_t* bgr, double* maxval);
+/* split + magnitude (ripcurrents.cpp:232-233) of n interleaved (x, y) pairs */
+int rc_field_magnitude(rc_ctx* ctx, const float* field, size_t n, float* mag);
+/* streamline_positions (module:44-59) */
+int rc_streamline_positions(rc_ctx* ctx, const float* field, int w, int h, float* density, int flags);
+
 /* ---- fused per-frame step (what main()'s loop body does between video.read and imshow) ----------- */
 
 /* rc_flow_push + rc_polar_hist + rc_thresholds + rc_classify_accumulate (+ rc_window_update when a window is

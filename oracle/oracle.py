@@ -9,6 +9,7 @@ Function <-> reference map (details in the C headers of each file):
   histogram()/thresholds()/classify_accumulate()   ripcurrents.cpp:319-439
   window_update()       main.cpp:1143-1153
   advect()/streakline_step()   pathlines.cpp:9-46, ripcurrents_module.cpp:486-679, Streakline.cpp:22-48
+  field_magnitude()/divide()/fmax()/normalize_jet()/positions()   ripcurrents.cpp:231-279, ripcurrents_module.cpp:13-59
 """
 import ctypes as C
 import os
@@ -26,7 +27,7 @@ ADV_PATHLINE, ADV_LEGACY, ADV_MODULE, ADV_CUT5, ADV_FIXED100, ADV_FIELD, ADV_GET
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("farneback_oracle.c", "aggregate_oracle.c", "advect_oracle.c", "ingest_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("farneback_oracle.c", "aggregate_oracle.c", "advect_oracle.c", "ingest_oracle.c", "fields_oracle.c")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs if os.path.exists(s))):
         return _SO
@@ -45,6 +46,7 @@ def lib():
         _lib.rc_oracle_farneback.restype = C.c_int
         _lib.rc_oracle_layers.restype = C.c_int
         _lib.rc_oracle_pyr_layer.restype = C.c_int
+        _lib.rc_oracle_max.restype = C.c_double
     return _lib
 
 
@@ -219,3 +221,53 @@ def edges(mask):
     out = np.empty((h, w), np.uint8)
     lib().rc_oracle_edges(_p(mask), C.c_int(w), C.c_int(h), _p(out))
     return out
+
+
+def jet_lut():
+    lut = np.empty((256, 3), np.uint8)
+    lib().rc_oracle_jet_lut(_p(lut))
+    return lut
+
+
+def field_magnitude(field):
+    """split + magnitude of ripcurrents.cpp:232-233 on a (h, w, 2) displacement field."""
+    field = np.ascontiguousarray(field, np.float32)
+    out = np.empty(field.shape[:-1], np.float32)
+    lib().rc_oracle_field_magnitude(_p(field), C.c_size_t(out.size), _p(out))
+    return out
+
+
+def divide(a, b, div0_zero=False):
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    out = np.empty_like(a)
+    lib().rc_oracle_divide(_p(a), _p(b), C.c_size_t(a.size), C.c_int(1 if div0_zero else 0), _p(out))
+    return out
+
+
+def fmax(src):
+    """minMaxLoc(src, NULL, &max) (NaNs ignored, see fields_oracle.c)."""
+    src = np.ascontiguousarray(src, np.float32)
+    return float(lib().rc_oracle_max(_p(src), C.c_size_t(src.size)))
+
+
+def normalize_jet(src, maxval=None):
+    """module:13-29: convertTo(CV_8UC1, 255/max) + applyColorMap(JET) -> (max, gray, bgr)."""
+    src = np.ascontiguousarray(src, np.float32)
+    if maxval is None:
+        maxval = fmax(src)
+    gray = np.empty(src.shape, np.uint8); bgr = np.empty(src.shape + (3,), np.uint8)
+    with np.errstate(all="ignore"):
+        lib().rc_oracle_normalize_jet(_p(src), C.c_size_t(src.size), C.c_double(maxval), _p(gray), _p(bgr))
+    return maxval, gray, bgr
+
+
+def positions(field, density=None):
+    """streamline_positions (module:44-59); density=None mirrors the Mat::zeros of ripcurrents.cpp:261."""
+    field = np.ascontiguousarray(field, np.float32)
+    h, w, _ = field.shape
+    zero = density is None
+    if zero:
+        density = np.empty((h, w, 3), np.float32)
+    assert density.dtype == np.float32 and density.flags.c_contiguous
+    lib().rc_oracle_positions(_p(field), C.c_int(w), C.c_int(h), _p(density), C.c_int(1 if zero else 0))
+    return density

@@ -24,6 +24,7 @@ SYMBOLS = [
     "rc_thresholds", "rc_accumulator_reset", "rc_classify_accumulate", "rc_accumulator_get",
     "rc_accumulator_device", "rc_window_configure", "rc_window_update", "rc_window_get", "rc_window_device",
     "rc_subtract_mean", "rc_batch_hist", "rc_aggregate_last", "rc_accumulator_mask", "rc_mask_edges", "rc_ingest_bgr", "rc_submit_frames_bgr", "rc_hist_from_polar", "rc_create_flow", "rc_create_accumulationbuffer", "rc_advect", "rc_streakline_step", "rc_process_frame",
+    "rc_particle_fields", "rc_normalize_jet", "rc_ratio_jet", "rc_field_magnitude", "rc_streamline_positions",
 ]
 
 
@@ -359,6 +360,54 @@ class Context:
         self._chk(self.lib.rc_mask_edges(self.h, _ptr(m3), C.c_size_t(w), C.c_size_t(w * h), C.c_int(w), C.c_int(h),
                                          C.c_int(count), _ptr(out), C.c_size_t(w), C.c_size_t(w * h)))
         return out.reshape(shp)
+
+    # ---- derived particle fields (ripcurrents.cpp:231-279, module:13-59) ----
+    def particle_fields(self, field, dist, flags=0, density=True):
+        """field (h,w,2) f32 displacements, dist (h,w) f32 path lengths -> dict with streamfield, the three JET images,
+        the position scatter and the maxima."""
+        field = np.ascontiguousarray(field, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+        h, w, _ = field.shape
+        out = {"streamfield": np.empty((h, w), np.float32), "disp_bgr": np.empty((h, w, 3), np.uint8),
+               "motion_bgr": np.empty((h, w, 3), np.uint8), "ratio_bgr": np.empty((h, w, 3), np.uint8)}
+        dens = np.empty((h, w, 3), np.float32) if density else None
+        mx = (C.c_double * 3)()
+        self._chk(self.lib.rc_particle_fields(self.h, _ptr(field), _ptr(dist), C.c_int(w), C.c_int(h), C.c_int(flags),
+                                              _ptr(out["streamfield"]), _ptr(out["disp_bgr"]), _ptr(out["motion_bgr"]),
+                                              _ptr(out["ratio_bgr"]), _ptr(dens) if density else None, mx))
+        out["density"] = dens
+        out["max"] = (mx[0], mx[1], mx[2])
+        return out
+
+    def normalize_jet(self, src):
+        src = np.ascontiguousarray(src, np.float32)
+        gray = np.empty(src.shape, np.uint8); bgr = np.empty(src.shape + (3,), np.uint8)
+        mx = C.c_double()
+        self._chk(self.lib.rc_normalize_jet(self.h, _ptr(src), C.c_size_t(src.size), _ptr(gray), _ptr(bgr), C.byref(mx)))
+        return mx.value, gray, bgr
+
+    def ratio_jet(self, a, b, flags=0):
+        a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+        ratio = np.empty(a.shape, np.float32); gray = np.empty(a.shape, np.uint8); bgr = np.empty(a.shape + (3,), np.uint8)
+        mx = C.c_double()
+        self._chk(self.lib.rc_ratio_jet(self.h, _ptr(a), _ptr(b), C.c_size_t(a.size), C.c_int(flags), _ptr(ratio), _ptr(gray),
+                                        _ptr(bgr), C.byref(mx)))
+        return mx.value, ratio, gray, bgr
+
+    def field_magnitude(self, field):
+        field = np.ascontiguousarray(field, np.float32)
+        mag = np.empty(field.shape[:-1], np.float32)
+        self._chk(self.lib.rc_field_magnitude(self.h, _ptr(field), C.c_size_t(mag.size), _ptr(mag)))
+        return mag
+
+    def streamline_positions(self, field, density=None):
+        field = np.ascontiguousarray(field, np.float32)
+        h, w, _ = field.shape
+        keep = density is not None
+        if not keep:
+            density = np.empty((h, w, 3), np.float32)
+        self._chk(self.lib.rc_streamline_positions(self.h, _ptr(field), C.c_int(w), C.c_int(h), _ptr(density),
+                                                   C.c_int(2 if keep else 0)))
+        return density
 
     def ingest_bgr(self, bgr, dw, dh, flags=0):
         bgr = np.ascontiguousarray(bgr, np.uint8)

@@ -88,6 +88,7 @@ public:
     int channels() const { return CV_MAT_CN(type_); }
     size_t elemSize() const { return (size_t)CV_MAT_CN(type_) * (CV_MAT_DEPTH(type_) == CV_8U ? 1 : 4); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    bool isContinuous() const { return rows <= 1 || step == (size_t)cols * elemSize(); }
     Size size() const { return Size(cols, rows); }
     template <typename T> T* ptr(int r = 0, int c = 0) { return reinterpret_cast<T*>(data + (size_t)r * step) + c; }
     template <typename T> const T* ptr(int r = 0, int c = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step) + c; }

@@ -5,7 +5,8 @@
 //
 //   demo_main frames.raw W H N out.bin
 // frames.raw: N frames of W*H u8.  out.bin: per processed frame { float UPPER; int histsum; float acc_sum;
-// int mask_calm; float field_sum; } -- tests/test_gpu_cpp_dropin.py compares them with the CPU oracle.
+// int mask_calm; float field_sum; streak checksum; byte sums of the three JET images; density sum } --
+// tests/test_gpu_cpp_dropin.py compares them with the CPU oracle.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -46,6 +47,14 @@ int main(int argc, char** argv)
         rc::streamline_field_all(streamlines_mat, streamlines_distance, current, 2, 1, UPPER);   // :229-231
         Streakline::runAll(streaks, current);                                             // main.cpp:150-152
 
+        Mat streamfield, disp_color, motion_color, ratio_color;                           // :231-258 / main_old.cpp:373-386
+        rc::particle_fields(streamlines_mat, streamlines_distance, &streamfield, nullptr, nullptr, nullptr, nullptr);
+        streamline_displacement(streamfield, disp_color);
+        streamline_total_motion(streamlines_distance, motion_color);
+        streamline_ratio(streamfield, streamlines_distance, ratio_color);
+        Mat streamline_density = Mat::zeros(Size(W, H), CV_32FC3);                        // :261
+        streamline_positions(streamlines_mat, streamline_density);
+
         Mat polar;
         rc::flowToPolar(current, polar);                                                  // :305-309
         create_histogram(polar, hist, histsum, hist2d, histsum2d, UPPER, UPPER2d, prop_above_upper);   // :319-366
@@ -54,15 +63,22 @@ int main(int argc, char** argv)
         Mat out = Mat::zeros(Size(W, H), CV_32FC3), outmask = Mat::zeros(Size(W, H), CV_8UC1);   // :419-420
         create_accumulationbuffer(accumulator, accumulator2, out, outmask, framecount + 28);    // :414-439 (offset: crosses 30)
 
-        double acc_sum = 0, field_sum = 0; int calm = 0;
+        double acc_sum = 0, field_sum = 0, csum[3] = {0, 0, 0}, dsum = 0; int calm = 0;
         for (int y = 0; y < H; y++)
             for (int x = 0; x < W; x++) {
                 acc_sum += accumulator.ptr<Pixel3>(y)[x].x;
                 calm += outmask.ptr<uchar>(y)[x] == 255;
                 field_sum += streamlines_distance.ptr<float>(y)[x];
+                for (int k = 0; k < 3; k++) {
+                    csum[0] += disp_color.ptr<uchar>(y)[3 * x + k] * (k + 1);
+                    csum[1] += motion_color.ptr<uchar>(y)[3 * x + k] * (k + 1);
+                    csum[2] += ratio_color.ptr<uchar>(y)[3 * x + k] * (k + 1);
+                }
+                dsum += streamline_density.ptr<float>(y)[3 * x + 2];
             }
-        float rec[6] = {UPPER, (float)histsum, (float)acc_sum, (float)calm, (float)field_sum,
-                        streaks[0].vertices.back().x + streaks[1].vertices.back().y};
+        float rec[10] = {UPPER, (float)histsum, (float)acc_sum, (float)calm, (float)field_sum,
+                         streaks[0].vertices.back().x + streaks[1].vertices.back().y,
+                         (float)csum[0], (float)csum[1], (float)csum[2], (float)dsum};
         std::fwrite(rec, sizeof rec, 1, out_f);
     }
     std::fclose(out_f);

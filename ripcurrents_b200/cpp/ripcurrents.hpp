@@ -41,7 +41,18 @@ void streamline_field_all(cv::Mat& streamlines_mat, cv::Mat& streamlines_distanc
                           int iterations, float UPPER);                                    // ripcurrents.cpp:229-231
 void streamlines_all(Pixel2* pts, int n, const cv::Mat& flow, float dt, int iterations, float UPPER, int variant);
 void window_average(std::vector<cv::Mat>& buffer, int& currentBuffer, const cv::Mat& flow, cv::Mat& average); // main.cpp:1143-1153
+// ripcurrents.cpp:231-279 in one call: magnitude + the three normalised JET images + the position scatter (two passes
+// over 12 B/px instead of the reference's twelve); any output may be nullptr
+void particle_fields(const cv::Mat& streamlines_mat, const cv::Mat& streamlines_distance, cv::Mat* streamfield,
+                     cv::Mat* displacement_color, cv::Mat* motion_color, cv::Mat* ratio_color, cv::Mat* density,
+                     double maxes[3] = nullptr, int flags = 0);
 }  // namespace rc
+
+// ripcurrents_module.cpp:13-59 (main_old.cpp:373-386)
+void streamline_displacement(cv::Mat& streamfield, cv::Mat& streamoverlay_color);
+void streamline_total_motion(cv::Mat& streamlines_distance, cv::Mat& streamoverlay_color);
+void streamline_ratio(cv::Mat& streamfield, cv::Mat& streamlines_distance, cv::Mat& streamoverlay_color);
+void streamline_positions(cv::Mat& streamlines_mat, cv::Mat& streamline_density);
 
 void streamline_field(Pixel2* pt, float* distancetraveled, int xoffset, int yoffset, cv::Mat flow, float dt,
                       int iterations, float UPPER, float prop_above_upper[HIST_DIRECTIONS]);

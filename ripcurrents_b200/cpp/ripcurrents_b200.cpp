@@ -239,6 +239,67 @@ void create_edges(cv::Mat& outmask)
                         outmask.step, 0), "rc_mask_edges");
 }
 
+// ---- derived particle fields (ripcurrents_module.cpp:13-59) ----------------------------------------------------------
+namespace {
+cv::Mat dense(const cv::Mat& m) { return m.isContinuous() ? m : m.clone(); }
+}
+
+void streamline_displacement(cv::Mat& streamfield, cv::Mat& streamoverlay_color)
+{
+    require(streamfield.type() == CV_32FC1, "streamline_displacement: CV_32FC1 input required");
+    cv::Mat src = dense(streamfield);
+    streamoverlay_color.create(src.rows, src.cols, CV_8UC3);
+    check(rc_normalize_jet(rc::default_context(), src.ptr<float>(), (size_t)src.rows * src.cols, nullptr,
+                           streamoverlay_color.data, nullptr), "rc_normalize_jet");
+}
+
+void streamline_total_motion(cv::Mat& streamlines_distance, cv::Mat& streamoverlay_color)
+{
+    streamline_displacement(streamlines_distance, streamoverlay_color);        // module:23-29 is the same chain
+}
+
+void streamline_ratio(cv::Mat& streamfield, cv::Mat& streamlines_distance, cv::Mat& streamoverlay_color)
+{
+    require(streamfield.type() == CV_32FC1 && streamlines_distance.type() == CV_32FC1 &&
+            streamfield.rows == streamlines_distance.rows && streamfield.cols == streamlines_distance.cols,
+            "streamline_ratio: two CV_32FC1 images of one size required");
+    cv::Mat a = dense(streamfield), b = dense(streamlines_distance);
+    streamoverlay_color.create(a.rows, a.cols, CV_8UC3);
+    check(rc_ratio_jet(rc::default_context(), a.ptr<float>(), b.ptr<float>(), (size_t)a.rows * a.cols, 0, nullptr, nullptr,
+                       streamoverlay_color.data, nullptr), "rc_ratio_jet");
+}
+
+void streamline_positions(cv::Mat& streamlines_mat, cv::Mat& streamline_density)
+{
+    require(streamlines_mat.type() == CV_32FC2 && streamline_density.type() == CV_32FC3 && streamline_density.isContinuous() &&
+            streamline_density.rows == streamlines_mat.rows && streamline_density.cols == streamlines_mat.cols,
+            "streamline_positions: CV_32FC2 field and a dense CV_32FC3 density of the same size required");
+    cv::Mat f = dense(streamlines_mat);
+    check(rc_streamline_positions(rc::default_context(), f.ptr<float>(), f.cols, f.rows, streamline_density.ptr<float>(),
+                                  RC_FIELDS_KEEP_DENSITY), "rc_streamline_positions");
+}
+
+void rc::particle_fields(const cv::Mat& streamlines_mat, const cv::Mat& streamlines_distance, cv::Mat* streamfield,
+                         cv::Mat* displacement_color, cv::Mat* motion_color, cv::Mat* ratio_color, cv::Mat* density,
+                         double maxes[3], int flags)
+{
+    require(streamlines_mat.type() == CV_32FC2 && streamlines_distance.type() == CV_32FC1 &&
+            streamlines_mat.rows == streamlines_distance.rows && streamlines_mat.cols == streamlines_distance.cols,
+            "particle_fields: CV_32FC2 displacements and CV_32FC1 distances of one size required");
+    cv::Mat f = dense(streamlines_mat), d = dense(streamlines_distance);
+    const int r = f.rows, c = f.cols;
+    if (streamfield) streamfield->create(r, c, CV_32FC1);
+    if (displacement_color) displacement_color->create(r, c, CV_8UC3);
+    if (motion_color) motion_color->create(r, c, CV_8UC3);
+    if (ratio_color) ratio_color->create(r, c, CV_8UC3);
+    if (density && !(flags & RC_FIELDS_KEEP_DENSITY)) density->create(r, c, CV_32FC3);
+    check(rc_particle_fields(rc::default_context(), f.ptr<float>(), d.ptr<float>(), c, r, flags,
+                             streamfield ? streamfield->ptr<float>() : nullptr,
+                             displacement_color ? displacement_color->data : nullptr, motion_color ? motion_color->data : nullptr,
+                             ratio_color ? ratio_color->data : nullptr, density ? density->ptr<float>() : nullptr, maxes),
+          "rc_particle_fields");
+}
+
 void subtructAverage(cv::Mat& current)
 {
     require(current.type() == CV_32FC2, "subtructAverage: CV_32FC2 flow required");

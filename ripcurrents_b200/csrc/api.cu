@@ -11,7 +11,8 @@
 
 const char* const rc_kernel_names[K_COUNT] = {"reserved", "pyramid", "polyexp", "update_matrices", "flow_iter_fused",
                                               "flow_iter_final", "flow_layer_fused", "polar_hist", "thresholds",
-                                              "classify", "window_mean", "advect", "streakline", "misc"};
+                                              "classify", "window_mean", "advect", "streakline", "misc",
+                                              "particle_fields"};
 
 namespace {
 
@@ -314,6 +315,58 @@ int finish_slot(rc_ctx* c, int slot)
 }  // namespace
 
 // =====================================================================================================
+namespace {
+// Host pointers are staged through one scratch arena (d_tmp); device pointers pass through.
+struct Stager {
+    rc_ctx* c; char* base = nullptr; size_t off = 0;
+    struct Out { void* host; void* dev; size_t bytes; };
+    std::vector<Out> outs;
+    static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+    template <class T> const T* in(const T* p, size_t bytes)
+    {
+        if (!p || is_device_ptr(p)) return p;
+        T* d = reinterpret_cast<T*>(base + off); off += pad(bytes);
+        cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, c->stream);
+        return d;
+    }
+    template <class T> T* out(T* p, size_t bytes, bool also_in = false)
+    {
+        if (!p || is_device_ptr(p)) return p;
+        T* d = reinterpret_cast<T*>(base + off); off += pad(bytes);
+        if (also_in) cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, c->stream);
+        outs.push_back(Out{p, d, bytes});
+        return d;
+    }
+    int finish()
+    {
+        for (auto& o : outs) cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, c->stream);
+        if (!outs.empty() && cudaStreamSynchronize(c->stream) != cudaSuccess)
+            return fail(c, RC_ERR_CUDA, "particle fields: %s", cudaGetErrorString(cudaGetLastError()));
+        return RC_OK;
+    }
+};
+
+int fields_impl(rc_ctx* c, const float* field, const float* src0, const float* dist, size_t n, int flags, int want,
+                float* mag_out, float* ratio_out, uint8_t* const gray[3], uint8_t* const bgr[3], double* maxes)
+{
+    cudaSetDevice(c->device);
+    const size_t need = 36 * n + 16 * 256;     // upper bound: every array on the host
+    int rc = ensure(c, &c->d_tmp, &c->d_tmp_cap, need); if (rc) return rc;
+    Stager st{c, reinterpret_cast<char*>(c->d_tmp)};
+    unsigned* d_enc = reinterpret_cast<unsigned*>(st.base); st.off = 256;
+    double* d_max = nullptr;
+    if (maxes) { d_max = reinterpret_cast<double*>(st.base + st.off); st.off += 256; st.outs.push_back({maxes, d_max, 24}); }
+    field = st.in(field, n * 8); src0 = st.in(src0, n * 4); dist = st.in(dist, n * 4);
+    mag_out = st.out(mag_out, n * 4); ratio_out = st.out(ratio_out, n * 4);
+    uint8_t* g[3]; uint8_t* b[3];
+    for (int k = 0; k < 3; k++) { g[k] = st.out(gray[k], n); b[k] = st.out(bgr[k], 3 * n); }
+    rc_launch_fields(c, field, src0, dist, n, (flags & RC_FIELDS_DIV_ZERO_IS_ZERO) ? 1 : 0, want, mag_out, ratio_out, g, b,
+                     d_enc, d_max);
+    CHECK_LAUNCH(c);
+    return st.finish();
+}
+}  // namespace
+
 extern "C" {
 
 int rc_version(void) { return RC_VERSION; }
@@ -1131,6 +1184,67 @@ int rc_mask_edges(rc_ctx* c, const uint8_t* masks, size_t mask_step, size_t mask
                                           cudaMemcpyDeviceToHost, c->stream));
     if (hin || hout) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return RC_OK;
+}
+
+// ---- derived particle fields ---------------------------------------------------------------
+int rc_particle_fields(rc_ctx* c, const float* field, const float* dist, int w, int h, int flags, float* streamfield,
+                       uint8_t* disp_bgr, uint8_t* motion_bgr, uint8_t* ratio_bgr, float* density, double* maxes)
+{
+    if (!c || !field || w < 1 || h < 1) return RC_ERR_INVALID;
+    if (!dist && (motion_bgr || ratio_bgr)) return fail(c, RC_ERR_INVALID, "motion/ratio outputs need the distance field%s");
+    const size_t n = (size_t)w * h;
+    uint8_t* gray[3] = {nullptr, nullptr, nullptr};
+    uint8_t* bgr[3] = {disp_bgr, motion_bgr, ratio_bgr};
+    const int want = 1 | (dist ? 6 : 0);
+    double m[3];
+    int rc = fields_impl(c, field, nullptr, dist, n, flags, want, streamfield, nullptr, gray, bgr, maxes ? m : nullptr);
+    if (rc) return rc;
+    if (maxes) { maxes[0] = m[0]; maxes[1] = dist ? m[1] : 0.0; maxes[2] = dist ? m[2] : 0.0; }
+    if (density) return rc_streamline_positions(c, field, w, h, density, flags);
+    return RC_OK;
+}
+
+int rc_normalize_jet(rc_ctx* c, const float* src, size_t n, uint8_t* gray, uint8_t* bgr, double* maxval)
+{
+    if (!c || !src || n < 1) return RC_ERR_INVALID;
+    uint8_t* g[3] = {gray, nullptr, nullptr}; uint8_t* b[3] = {bgr, nullptr, nullptr};
+    double m[3];
+    int rc = fields_impl(c, nullptr, src, nullptr, n, 0, 1, nullptr, nullptr, g, b, maxval ? m : nullptr);
+    if (!rc && maxval) *maxval = m[0];
+    return rc;
+}
+
+int rc_ratio_jet(rc_ctx* c, const float* a, const float* b, size_t n, int flags, float* ratio, uint8_t* gray, uint8_t* bgr,
+                 double* maxval)
+{
+    if (!c || !a || !b || n < 1) return RC_ERR_INVALID;
+    uint8_t* g[3] = {nullptr, nullptr, gray}; uint8_t* o[3] = {nullptr, nullptr, bgr};
+    double m[3];
+    int rc = fields_impl(c, nullptr, a, b, n, flags, 4, nullptr, ratio, g, o, maxval ? m : nullptr);
+    if (!rc && maxval) *maxval = m[2];
+    return rc;
+}
+
+int rc_field_magnitude(rc_ctx* c, const float* field, size_t n, float* mag)
+{
+    if (!c || !field || !mag || n < 1) return RC_ERR_INVALID;
+    uint8_t* z[3] = {nullptr, nullptr, nullptr};
+    return fields_impl(c, field, nullptr, nullptr, n, 0, 0, mag, nullptr, z, z, nullptr);
+}
+
+int rc_streamline_positions(rc_ctx* c, const float* field, int w, int h, float* density, int flags)
+{
+    if (!c || !field || !density || w < 1 || h < 1) return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    const size_t n = (size_t)w * h;
+    int rc = ensure(c, &c->d_tmp2, &c->d_tmp2_cap, 20 * n + 512); if (rc) return rc;
+    Stager st{c, reinterpret_cast<char*>(c->d_tmp2)};
+    const bool keep = (flags & RC_FIELDS_KEEP_DENSITY) != 0;
+    field = st.in(field, n * 8);
+    density = st.out(density, n * 12, keep);
+    rc_launch_positions(c, field, w, h, density, keep ? 0 : 1);
+    CHECK_LAUNCH(c);
+    return st.finish();
 }
 
 // ---- fused per-frame / per-batch step -------------------------------------------------------------------------

@@ -19,7 +19,7 @@
 // kernel classes for rc_profile_* (per-launch CUDA-event timing) -- order matches rc_kernel_names[]
 enum RcKernelId { K_RESERVED = 0, K_PYR_V, K_POLYEXP, K_UPDATE_MATRICES, K_FLOW_ITER_FUSED, K_FLOW_ITER_FINAL,
                   K_FLOW_LAYER, K_POLAR_HIST, K_THRESHOLDS, K_CLASSIFY, K_WINDOW, K_ADVECT, K_STREAKLINE, K_MISC,
-                  K_COUNT };
+                  K_FIELDS, K_COUNT };
 extern const char* const rc_kernel_names[K_COUNT];
 
 struct PolyCoef {          // polynomial-expansion kernels; entries beyond n are zero
@@ -209,6 +209,12 @@ void rc_launch_ingest_bgr(rc_ctx* c, const uint8_t* bgr, size_t step, size_t fst
 
 void rc_launch_edges(rc_ctx* c, const uint8_t* mask, size_t step, size_t stride, int w, int h, uint8_t* out, size_t ostep,
                      size_t ostride, int nb);
+
+// ---- fields.cu -------------------------------------------------------------------------------------
+void rc_launch_fields(rc_ctx* c, const float* field, const float* src0, const float* dist, size_t n, int div0_zero, int want,
+                      float* mag_out, float* ratio_out, uint8_t* const gray[3], uint8_t* const bgr[3], unsigned* d_maxenc,
+                      double* d_max);
+void rc_launch_positions(rc_ctx* c, const float* field, int w, int h, float* density, int zero_first);
 
 // ---- advect.cu -------------------------------------------------------------------------------------
 void rc_launch_advect(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float* seeds, size_t n, float dt,

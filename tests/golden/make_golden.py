@@ -61,6 +61,31 @@ def ingest():
     np.savez_compressed(os.path.join(HERE, "ingest.npz"), cv2_version=np.array(cv2.__version__), **out)
 
 
+def fields():
+    # derived particle fields: cv2 with OpenCV's own kernels (setUseOptimized(False): the IPP
+    # magnitude differs by <= 2 ulp and cannot be restated) on a synthetic displacement / path-length pair
+    cv2.setUseOptimized(False)
+    rng = np.random.default_rng(11)
+    h, w = 48, 67
+    field = (rng.standard_normal((h, w, 2)) * 6).astype(np.float32)
+    field[:4] = 0                                                   # particles that never moved
+    sf = cv2.magnitude(field[..., 0].copy(), field[..., 1].copy())
+    dist = (sf + np.abs(rng.standard_normal((h, w)) * 5)).astype(np.float32)
+    dist[:4] = 1.0                                                  # keep the divisor non-zero: NaN-free fixture
+    out = {"field": field, "dist": dist, "streamfield": sf}
+    ratio = cv2.divide(sf, dist)
+    for name, src in (("disp", sf), ("motion", dist), ("ratio", ratio)):
+        mx = cv2.minMaxLoc(src)[1]
+        gray = cv2.convertScaleAbs(src, alpha=255 / mx)             # == Mat::convertTo(CV_8UC1, 255/max) for src >= 0
+        out[name + "_max"] = np.float64(mx); out[name + "_gray"] = gray
+        out[name + "_bgr"] = cv2.applyColorMap(gray, cv2.COLORMAP_JET)
+    out["ratio"] = ratio
+    out["jet_lut"] = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, -1), cv2.COLORMAP_JET).reshape(256, 3)
+    cv2.setUseOptimized(True)
+    np.savez_compressed(os.path.join(HERE, "fields.npz"), cv2_version=np.array(cv2.__version__), **out)
+
+
 if __name__ == "__main__":
     main()
     ingest()
+    fields()

@@ -18,7 +18,7 @@ def test_cpp_frame_loop_matches_oracle(tmp_path, oracle):
     raw = tmp_path / "frames.raw"; out = tmp_path / "out.bin"
     fr.tofile(raw)
     subprocess.check_call([demo, str(raw), str(w), str(h), str(n), str(out)], timeout=300)
-    rec = np.fromfile(out, np.float32).reshape(n - 1, 6)
+    rec = np.fromfile(out, np.float32).reshape(n - 1, 10)
 
     ctx = Context(0)
     P = (0.5, 2, 3, 2, 15, 1.2, 0)
@@ -34,6 +34,10 @@ def test_cpp_frame_loop_matches_oracle(tmp_path, oracle):
         flow = ctx.farneback(fr[i - 1], fr[i], *P).copy()
         oracle.advect(flow, disp, 2.0, 1, float(upper), oracle.ADV_FIELD, dist=dist)
         oracle.streakline_step(flow, em, verts, cnt)
+        sf = oracle.field_magnitude(disp.reshape(h, w, 2)); d2 = dist.reshape(h, w)
+        with np.errstate(all="ignore"):
+            fields = [oracle.normalize_jet(sf)[2], oracle.normalize_jet(d2)[2], oracle.normalize_jet(oracle.divide(sf, d2))[2]]
+        dens = oracle.positions(disp.reshape(h, w, 2))
         oracle.histogram(flow, st)
         upper, _, _ = oracle.thresholds(st)
         mask, _, _ = oracle.classify_accumulate(flow, upper, i + 28, acc)
@@ -44,4 +48,8 @@ def test_cpp_frame_loop_matches_oracle(tmp_path, oracle):
         assert rec[i - 1, 3] == np.float32((mask == 255).sum()), i
         assert np.isclose(rec[i - 1, 4], dist.astype(np.float64).sum(), rtol=1e-6), i
         assert rec[i - 1, 5] == np.float32(verts[0, cnt[0] - 1, 0] + verts[1, cnt[1] - 1, 1]), i
+        # derived particle fields (ripcurrents.cpp:231-279) from the state before this frame's histogram update
+        for k, img in enumerate(fields):
+            assert rec[i - 1, 6 + k] == np.float32((img.astype(np.float64) * [1, 2, 3]).sum()), (i, k)
+        assert rec[i - 1, 9] == np.float32(dens[..., 2].astype(np.float64).sum()), i
     ctx.close()

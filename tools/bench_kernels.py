@@ -74,6 +74,16 @@ def main():
                                                                                       cnt.data_ptr(), E=E, cap=cap)),
          E * (cap - 1), "vertex_steps")
 
+    # ---- derived particle fields of the 1080p state (3 JET images + magnitude + position scatter)
+    pf = torch.randn((h * w, 2), device=dev) * 6
+    pd = pf.norm(dim=1) + torch.rand(h * w, device=dev) * 5
+    sf = torch.empty(h * w, device=dev); dens = torch.empty(h * w * 3, device=dev)
+    imgs = [torch.empty(h * w * 3, dtype=torch.uint8, device=dev) for _ in range(3)]
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    emit("particle_fields_1080p", timed(c, lambda: c._chk(c.lib.rc_particle_fields(
+        c.h, vp(pf), vp(pd), C.c_int(w), C.c_int(h), C.c_int(0), vp(sf), vp(imgs[0]), vp(imgs[1]), vp(imgs[2]), vp(dens), None))),
+        1, "frames")
+
     # ---- ingest and mask clean-up
     bgr = torch.randint(0, 256, (8, 1080, 1920, 3), dtype=torch.uint8, device=dev)
     gray = torch.empty((8, 480, 640), dtype=torch.uint8, device=dev)
