@@ -271,6 +271,29 @@ int rc_field_magnitude(rc_ctx* ctx, const float* field, size_t n, float* mag);
 /* streamline_positions (module:44-59) */
 int rc_streamline_positions(rc_ctx* ctx, const float* field, int w, int h, float* density, int flags);
 
+/* ---- flow-derived diagnostics -----------------------------------------------------
+ * ripcurrents_module.cpp:900-1138.  Bit-exact against the CPU restatement of the reference as GCC/x86-64 + glibc 2.39
+ * + cv2 4.13 execute it (float->uchar stores truncate and wrap; atan2f as libm computes it; 8-bit HSV->BGR as cv2's
+ * 32-pixel block path does: truncating, with FMAs -- RC_DIAG_HSV_NOFMA selects cv2's setUseOptimized(False) variant).
+ * The reference's function-local `static` maxima (each frame is normalised with the previous frame's maximum) are the
+ * in/out argument: a host float (in = previous maximum, out = this frame's; the call synchronises), or NULL to keep
+ * the state inside the context (starts at 0 like the reference's statics; the call stays asynchronous). */
+#define RC_DIAG_SEQUENTIAL_SUM 1   /* subtructMeanMagnitude: accumulate the mean in fp32 in pixel order on one thread,
+                                      as the reference's loop does (bit-exact, ~5 ms at 1080p); default: fp64 tree sum */
+#define RC_DIAG_HSV_NOFMA 2
+/* subtructMeanMagnitude (module:900-1015): v <- v/|v| * (|v| - mean|v|), in place (host or device flow); *meanval
+ * (optional) receives the mean magnitude.  The reference's printf diagnostics are not reproduced. */
+int rc_subtract_mean_magnitude(rc_ctx* ctx, float* flow, size_t flow_step, int w, int h, int flags, float* meanval);
+/* vectorToColor (module:1017-1057): hue = direction/2, saturation 255, value = |v| * 255 / max, cvtColor(HSV2BGR).
+ * flow == NULL: the context's last flow.  bgr: w*h*3 u8, host or device. */
+int rc_vector_to_color(rc_ctx* ctx, const float* flow, size_t flow_step, int w, int h, uint8_t* bgr, size_t bgr_step,
+                       float* max_displacement, int flags);
+/* shearRateToColor (module:1059-1138): Frobenius norm of the velocity Jacobian (central differences at +-10 px) as
+ * hue = 128 - norm * 128 / max on the interior; the border of the caller's image is left alone and then, like the
+ * interior, converted HSV->BGR (img is in/out, as in the reference). */
+int rc_shear_rate_to_color(rc_ctx* ctx, const float* flow, size_t flow_step, int w, int h, uint8_t* img, size_t img_step,
+                           float* max_frobenius, int flags);
+
 /* ---- fused per-frame step (what main()'s loop body does between video.read and imshow) ----------- */
 
 /* rc_flow_push + rc_polar_hist + rc_thresholds + rc_classify_accumulate (+ rc_window_update when a window is

@@ -9,6 +9,7 @@ Function <-> reference map (details in the C headers of each file):
   histogram()/thresholds()/classify_accumulate()   ripcurrents.cpp:319-439
   window_update()       main.cpp:1143-1153
   advect()/streakline_step()   pathlines.cpp:9-46, ripcurrents_module.cpp:486-679, Streakline.cpp:22-48
+  subtract_mean_magnitude()/vector_to_color()/shear_to_color()/hsv2bgr()   ripcurrents_module.cpp:900-1138
   field_magnitude()/divide()/fmax()/normalize_jet()/positions()   ripcurrents.cpp:231-279, ripcurrents_module.cpp:13-59
 """
 import ctypes as C
@@ -27,7 +28,7 @@ ADV_PATHLINE, ADV_LEGACY, ADV_MODULE, ADV_CUT5, ADV_FIXED100, ADV_FIELD, ADV_GET
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("farneback_oracle.c", "aggregate_oracle.c", "advect_oracle.c", "ingest_oracle.c", "fields_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("farneback_oracle.c", "aggregate_oracle.c", "advect_oracle.c", "ingest_oracle.c", "fields_oracle.c", "diag_oracle.c")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs if os.path.exists(s))):
         return _SO
@@ -47,6 +48,7 @@ def lib():
         _lib.rc_oracle_layers.restype = C.c_int
         _lib.rc_oracle_pyr_layer.restype = C.c_int
         _lib.rc_oracle_max.restype = C.c_double
+        _lib.rc_oracle_subtract_mean_magnitude.restype = C.c_float
     return _lib
 
 
@@ -271,3 +273,37 @@ def positions(field, density=None):
     assert density.dtype == np.float32 and density.flags.c_contiguous
     lib().rc_oracle_positions(_p(field), C.c_int(w), C.c_int(h), _p(density), C.c_int(1 if zero else 0))
     return density
+
+
+def hsv2bgr(hsv, fma=True):
+    """cvtColor(COLOR_HSV2BGR) on 8-bit pixels (cv2's block path, see diag_oracle.c)."""
+    hsv = np.ascontiguousarray(hsv, np.uint8)
+    out = np.empty_like(hsv)
+    lib().rc_oracle_hsv2bgr(_p(hsv), C.c_size_t(hsv.size // 3), _p(out), C.c_int(1 if fma else 0))
+    return out
+
+
+def subtract_mean_magnitude(flow):
+    """subtructMeanMagnitude (module:900-1015), in place; returns meanval."""
+    assert flow.dtype == np.float32 and flow.flags.c_contiguous
+    return float(lib().rc_oracle_subtract_mean_magnitude(_p(flow), C.c_size_t(flow.size // 2)))
+
+
+def vector_to_color(flow, max_displacement, fma=True):
+    """vectorToColor (module:1017-1057) -> (hsv, bgr, new max_displacement)."""
+    flow = np.ascontiguousarray(flow, np.float32)
+    h, w, _ = flow.shape
+    hsv = np.empty((h, w, 3), np.uint8); bgr = np.empty((h, w, 3), np.uint8)
+    m = C.c_float(max_displacement)
+    lib().rc_oracle_vector_to_color(_p(flow), C.c_int(w), C.c_int(h), _p(hsv), _p(bgr), C.byref(m), C.c_int(1 if fma else 0))
+    return hsv, bgr, m.value
+
+
+def shear_to_color(flow, img, max_frobenius, fma=True):
+    """shearRateToColor (module:1059-1138); img (h,w,3) u8 is updated in place -> new max_frobeniusNorm."""
+    flow = np.ascontiguousarray(flow, np.float32)
+    h, w, _ = flow.shape
+    assert img.dtype == np.uint8 and img.flags.c_contiguous and img.shape == (h, w, 3)
+    m = C.c_float(max_frobenius)
+    lib().rc_oracle_shear_to_color(_p(flow), C.c_int(w), C.c_int(h), _p(img), C.byref(m), C.c_int(1 if fma else 0))
+    return m.value

@@ -12,13 +12,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libripcurrents_b200.so")
-SOURCES = ["farneback.cu", "aggregate.cu", "advect.cu", "compat.cu", "fields.cu", "api.cu"]
+SOURCES = ["farneback.cu", "aggregate.cu", "advect.cu", "compat.cu", "fields.cu", "diag.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall", "-Xptxas", "-v"]
 # farneback.cu holds both arithmetic modes: its strict code is written with __fmul_rn/__fadd_rn intrinsics (never
 # contracted) and its fast code wants FMA contraction; the other files restate reference arithmetic in which every
 # product and sum rounds separately, so they are compiled with contraction off.
-EXTRA = {"farneback.cu": [], "aggregate.cu": ["-fmad=false"], "advect.cu": ["-fmad=false"], "compat.cu": ["-fmad=false"], "fields.cu": ["-fmad=false"], "api.cu": ["-fmad=false"]}
+EXTRA = {"farneback.cu": [], "aggregate.cu": ["-fmad=false"], "advect.cu": ["-fmad=false"], "compat.cu": ["-fmad=false"], "fields.cu": ["-fmad=false"], "diag.cu": ["-fmad=false"], "api.cu": ["-fmad=false"]}
 
 
 def _nvcc():

@@ -25,6 +25,7 @@ SYMBOLS = [
     "rc_accumulator_device", "rc_window_configure", "rc_window_update", "rc_window_get", "rc_window_device",
     "rc_subtract_mean", "rc_batch_hist", "rc_aggregate_last", "rc_accumulator_mask", "rc_mask_edges", "rc_ingest_bgr", "rc_submit_frames_bgr", "rc_hist_from_polar", "rc_create_flow", "rc_create_accumulationbuffer", "rc_advect", "rc_streakline_step", "rc_process_frame",
     "rc_particle_fields", "rc_normalize_jet", "rc_ratio_jet", "rc_field_magnitude", "rc_streamline_positions",
+    "rc_subtract_mean_magnitude", "rc_vector_to_color", "rc_shear_rate_to_color",
 ]
 
 
@@ -408,6 +409,38 @@ class Context:
         self._chk(self.lib.rc_streamline_positions(self.h, _ptr(field), C.c_int(w), C.c_int(h), _ptr(density),
                                                    C.c_int(2 if keep else 0)))
         return density
+
+    # ---- flow-derived diagnostics (ripcurrents_module.cpp:900-1138) ----
+    def subtract_mean_magnitude(self, flow, flags=0):
+        """In place on a (h,w,2) f32 numpy flow; returns meanval."""
+        assert isinstance(flow, np.ndarray) and flow.dtype == np.float32 and flow.flags.c_contiguous
+        h, w, _ = flow.shape
+        mv = C.c_float()
+        self._chk(self.lib.rc_subtract_mean_magnitude(self.h, _ptr(flow), C.c_size_t(w * 8), C.c_int(w), C.c_int(h),
+                                                      C.c_int(flags), C.byref(mv)))
+        return mv.value
+
+    def vector_to_color(self, flow, max_displacement, flags=0):
+        """-> (bgr, new max_displacement); max_displacement=None keeps the state in the context."""
+        flow = np.ascontiguousarray(flow, np.float32)
+        h, w, _ = flow.shape
+        bgr = np.empty((h, w, 3), np.uint8)
+        m = C.c_float(max_displacement if max_displacement is not None else 0.0)
+        self._chk(self.lib.rc_vector_to_color(self.h, _ptr(flow), C.c_size_t(w * 8), C.c_int(w), C.c_int(h), _ptr(bgr),
+                                              C.c_size_t(w * 3), C.byref(m) if max_displacement is not None else None,
+                                              C.c_int(flags)))
+        return bgr, (m.value if max_displacement is not None else None)
+
+    def shear_rate_to_color(self, flow, img, max_frobenius, flags=0):
+        """img (h,w,3) u8 numpy is updated in place -> new max_frobeniusNorm (None keeps the state in the context)."""
+        flow = np.ascontiguousarray(flow, np.float32)
+        h, w, _ = flow.shape
+        assert img.dtype == np.uint8 and img.flags.c_contiguous and img.shape == (h, w, 3)
+        m = C.c_float(max_frobenius if max_frobenius is not None else 0.0)
+        self._chk(self.lib.rc_shear_rate_to_color(self.h, _ptr(flow), C.c_size_t(w * 8), C.c_int(w), C.c_int(h), _ptr(img),
+                                                  C.c_size_t(w * 3), C.byref(m) if max_frobenius is not None else None,
+                                                  C.c_int(flags)))
+        return m.value if max_frobenius is not None else None
 
     def ingest_bgr(self, bgr, dw, dh, flags=0):
         bgr = np.ascontiguousarray(bgr, np.uint8)

@@ -5,7 +5,8 @@
 //
 //   demo_main frames.raw W H N out.bin
 // frames.raw: N frames of W*H u8.  out.bin: per processed frame { float UPPER; int histsum; float acc_sum;
-// int mask_calm; float field_sum; streak checksum; byte sums of the three JET images; density sum } --
+// int mask_calm; float field_sum; streak checksum; byte sums of the three JET images; density sum;
+// byte sums of vectorToColor / shearRateToColor; sum of the mean-magnitude-centred flow } --
 // tests/test_gpu_cpp_dropin.py compares them with the CPU oracle.
 #include <cstdio>
 #include <cstdlib>
@@ -33,6 +34,7 @@ int main(int argc, char** argv)
     static int hist2d[HIST_DIRECTIONS][HIST_BINS]; int histsum2d[HIST_DIRECTIONS] = {0}; // :151-152
     float UPPER2d[HIST_DIRECTIONS] = {0}, prop_above_upper[HIST_DIRECTIONS] = {0};       // :153-154
     Mat streamlines_mat = Mat::zeros(H, W, CV_32FC2), streamlines_distance = Mat::zeros(H, W, CV_32FC1);   // :164-165
+    Mat vector_color = Mat::zeros(Size(W, H), CV_8UC3), shear_color = Mat::zeros(Size(W, H), CV_8UC3);
     std::vector<Streakline> streaks;
     streaks.push_back(Streakline(Pixel2(W * 0.3f, H * 0.4f)));
     streaks.push_back(Streakline(Pixel2(W * 0.6f, H * 0.5f)));
@@ -55,6 +57,11 @@ int main(int argc, char** argv)
         Mat streamline_density = Mat::zeros(Size(W, H), CV_32FC3);                        // :261
         streamline_positions(streamlines_mat, streamline_density);
 
+        vectorToColor(current, vector_color);                                             // main.cpp:629,761,1156 (module:1017)
+        shearRateToColor(current, shear_color);                                           // main.cpp:1518 (module:1059)
+        Mat centred = current.clone();
+        subtructMeanMagnitude(centred);                                                   // module:900 (main.cpp:1130)
+
         Mat polar;
         rc::flowToPolar(current, polar);                                                  // :305-309
         create_histogram(polar, hist, histsum, hist2d, histsum2d, UPPER, UPPER2d, prop_above_upper);   // :319-366
@@ -63,7 +70,7 @@ int main(int argc, char** argv)
         Mat out = Mat::zeros(Size(W, H), CV_32FC3), outmask = Mat::zeros(Size(W, H), CV_8UC1);   // :419-420
         create_accumulationbuffer(accumulator, accumulator2, out, outmask, framecount + 28);    // :414-439 (offset: crosses 30)
 
-        double acc_sum = 0, field_sum = 0, csum[3] = {0, 0, 0}, dsum = 0; int calm = 0;
+        double acc_sum = 0, field_sum = 0, csum[3] = {0, 0, 0}, dsum = 0, vsum = 0, ssum = 0, msum = 0; int calm = 0;
         for (int y = 0; y < H; y++)
             for (int x = 0; x < W; x++) {
                 acc_sum += accumulator.ptr<Pixel3>(y)[x].x;
@@ -75,10 +82,16 @@ int main(int argc, char** argv)
                     csum[2] += ratio_color.ptr<uchar>(y)[3 * x + k] * (k + 1);
                 }
                 dsum += streamline_density.ptr<float>(y)[3 * x + 2];
+                for (int k = 0; k < 3; k++) {
+                    vsum += vector_color.ptr<uchar>(y)[3 * x + k] * (k + 1);
+                    ssum += shear_color.ptr<uchar>(y)[3 * x + k] * (k + 1);
+                }
+                msum += centred.ptr<float>(y)[2 * x] + 2.0 * centred.ptr<float>(y)[2 * x + 1];
             }
-        float rec[10] = {UPPER, (float)histsum, (float)acc_sum, (float)calm, (float)field_sum,
+        float rec[13] = {UPPER, (float)histsum, (float)acc_sum, (float)calm, (float)field_sum,
                          streaks[0].vertices.back().x + streaks[1].vertices.back().y,
-                         (float)csum[0], (float)csum[1], (float)csum[2], (float)dsum};
+                         (float)csum[0], (float)csum[1], (float)csum[2], (float)dsum,
+                         (float)vsum, (float)ssum, (float)msum};
         std::fwrite(rec, sizeof rec, 1, out_f);
     }
     std::fclose(out_f);

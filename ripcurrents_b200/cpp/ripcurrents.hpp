@@ -53,6 +53,11 @@ void streamline_displacement(cv::Mat& streamfield, cv::Mat& streamoverlay_color)
 void streamline_total_motion(cv::Mat& streamlines_distance, cv::Mat& streamoverlay_color);
 void streamline_ratio(cv::Mat& streamfield, cv::Mat& streamlines_distance, cv::Mat& streamoverlay_color);
 void streamline_positions(cv::Mat& streamlines_mat, cv::Mat& streamline_density);
+// ripcurrents_module.cpp:900-1138.  The reference's function-local statics (previous frame's maxima) live in the
+// default context; they start at 0 as in the reference.
+void subtructMeanMagnitude(cv::Mat& current);
+void vectorToColor(cv::Mat& current, cv::Mat& outImg);
+void shearRateToColor(cv::Mat& current, cv::Mat& outImg);
 
 void streamline_field(Pixel2* pt, float* distancetraveled, int xoffset, int yoffset, cv::Mat flow, float dt,
                       int iterations, float UPPER, float prop_above_upper[HIST_DIRECTIONS]);

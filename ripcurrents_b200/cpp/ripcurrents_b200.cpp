@@ -300,6 +300,32 @@ void rc::particle_fields(const cv::Mat& streamlines_mat, const cv::Mat& streamli
           "rc_particle_fields");
 }
 
+// ---- flow-derived diagnostics (ripcurrents_module.cpp:900-1138) -----------------------------------------------------
+void subtructMeanMagnitude(cv::Mat& current)
+{
+    require(current.type() == CV_32FC2, "subtructMeanMagnitude: CV_32FC2 flow required");
+    check(rc_subtract_mean_magnitude(rc::default_context(), current.ptr<float>(), current.step, current.cols, current.rows,
+                                     RC_DIAG_SEQUENTIAL_SUM, nullptr), "rc_subtract_mean_magnitude");
+}
+
+void vectorToColor(cv::Mat& current, cv::Mat& outImg)
+{
+    require(current.type() == CV_32FC2 && outImg.type() == CV_8UC3 && outImg.rows == current.rows && outImg.cols == current.cols,
+            "vectorToColor: CV_32FC2 flow and CV_8UC3 image of the same size required");
+    check(rc_vector_to_color(rc::default_context(), current.ptr<float>(), current.step, current.cols, current.rows, outImg.data,
+                             outImg.step, nullptr, 0), "rc_vector_to_color");
+    check(rc_synchronize(rc::default_context()), "rc_synchronize");
+}
+
+void shearRateToColor(cv::Mat& current, cv::Mat& outImg)
+{
+    require(current.type() == CV_32FC2 && outImg.type() == CV_8UC3 && outImg.rows == current.rows && outImg.cols == current.cols,
+            "shearRateToColor: CV_32FC2 flow and CV_8UC3 image of the same size required");
+    check(rc_shear_rate_to_color(rc::default_context(), current.ptr<float>(), current.step, current.cols, current.rows,
+                                 outImg.data, outImg.step, nullptr, 0), "rc_shear_rate_to_color");
+    check(rc_synchronize(rc::default_context()), "rc_synchronize");
+}
+
 void subtructAverage(cv::Mat& current)
 {
     require(current.type() == CV_32FC2, "subtructAverage: CV_32FC2 flow required");

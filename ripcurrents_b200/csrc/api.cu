@@ -12,7 +12,7 @@
 const char* const rc_kernel_names[K_COUNT] = {"reserved", "pyramid", "polyexp", "update_matrices", "flow_iter_fused",
                                               "flow_iter_final", "flow_layer_fused", "polar_hist", "thresholds",
                                               "classify", "window_mean", "advect", "streakline", "misc",
-                                              "particle_fields"};
+                                              "particle_fields", "diagnostics"};
 
 namespace {
 
@@ -416,7 +416,7 @@ void rc_destroy(rc_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     free_farneback(c);
-    void* bufs[] = {c->d_bgr[0], c->d_bgr[1], c->d_tmp, c->d_tmp2, c->d_hist2d, c->d_thr, c->d_acc, c->d_cls, c->d_swin_ring, c->d_swin_avg};
+    void* bufs[] = {c->d_bgr[0], c->d_bgr[1], c->d_tmp, c->d_tmp2, c->d_diag, c->d_hist2d, c->d_thr, c->d_acc, c->d_cls, c->d_swin_ring, c->d_swin_avg};
     for (void* p : bufs) if (p) cudaFree(p);
     prof_drain(c);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -1245,6 +1245,82 @@ int rc_streamline_positions(rc_ctx* c, const float* field, int w, int h, float* 
     rc_launch_positions(c, field, w, h, density, keep ? 0 : 1);
     CHECK_LAUNCH(c);
     return st.finish();
+}
+
+// ---- flow-derived diagnostics -------------------------------------------------------------
+static int ensure_diag(rc_ctx* c)
+{
+    if (c->d_diag) return RC_OK;
+    const size_t bytes = 64 + 148 * 4 * sizeof(double);
+    if (cudaMalloc((void**)&c->d_diag, bytes) != cudaSuccess) { cudaGetLastError(); return fail(c, RC_ERR_NOMEM, "cudaMalloc failed%s"); }
+    CUDA_TRY(c, cudaMemsetAsync(c->d_diag, 0, bytes, c->stream));
+    return RC_OK;
+}
+
+int rc_subtract_mean_magnitude(rc_ctx* c, float* flow, size_t flow_step, int w, int h, int flags, float* meanval)
+{
+    if (!c || !flow || w < 1 || h < 1 || flow_step < (size_t)w * 8) return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    int rc = ensure_diag(c); if (rc) return rc;
+    const bool dev = is_device_ptr(flow);
+    float* d_flow = flow; size_t d_step = flow_step;
+    if (!dev) {
+        rc = ensure(c, &c->d_tmp, &c->d_tmp_cap, (size_t)w * h * 8); if (rc) return rc;
+        CUDA_TRY(c, cudaMemcpy2DAsync(c->d_tmp, (size_t)w * 8, flow, flow_step, (size_t)w * 8, h, cudaMemcpyHostToDevice, c->stream));
+        d_flow = reinterpret_cast<float*>(c->d_tmp); d_step = (size_t)w * 8;
+    }
+    rc_launch_sub_mean_magnitude(c, d_flow, d_step, w, h, (flags & RC_DIAG_SEQUENTIAL_SUM) ? 1 : 0,
+                                 reinterpret_cast<double*>(reinterpret_cast<char*>(c->d_diag) + 64), c->d_diag + 4);
+    CHECK_LAUNCH(c);
+    if (!dev) CUDA_TRY(c, cudaMemcpy2DAsync(flow, flow_step, d_flow, d_step, (size_t)w * 8, h, cudaMemcpyDeviceToHost, c->stream));
+    if (meanval) CUDA_TRY(c, cudaMemcpyAsync(meanval, c->d_diag + 4, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (meanval || !dev) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return RC_OK;
+}
+
+// shared body of the two colourisations: which = 0 vectorToColor, 1 shearRateToColor
+static int color_impl(rc_ctx* c, int which, const float* flow, size_t flow_step, int w, int h, uint8_t* img, size_t img_step,
+                      float* max_io, int flags)
+{
+    if (!c || !img) return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    int rc = ensure_diag(c); if (rc) return rc;
+    const float* d_flow; size_t d_step;
+    rc = stage_flow_in(c, flow, flow_step, w, h, &d_flow, &d_step); if (rc) return rc;
+    if (!flow) { w = c->prm.w; h = c->prm.h; }
+    if (img_step < (size_t)w * 3) return fail(c, RC_ERR_INVALID, "bad image step%s");
+    const bool himg = !is_device_ptr(img);
+    uint8_t* d_img = img; size_t d_istep = img_step;
+    if (himg) {
+        rc = ensure(c, &c->d_tmp2, &c->d_tmp2_cap, (size_t)w * h * 3); if (rc) return rc;
+        d_img = reinterpret_cast<uint8_t*>(c->d_tmp2); d_istep = (size_t)w * 3;
+        if (which == 1)       // in/out: the border keeps the caller's pixels
+            CUDA_TRY(c, cudaMemcpy2DAsync(d_img, d_istep, img, img_step, (size_t)w * 3, h, cudaMemcpyHostToDevice, c->stream));
+    }
+    float* prev = c->d_diag + 2 * which;
+    unsigned* next = reinterpret_cast<unsigned*>(c->d_diag + 2 * which + 1);
+    if (max_io) CUDA_TRY(c, cudaMemcpyAsync(prev, max_io, 4, cudaMemcpyHostToDevice, c->stream));
+    const int fma = (flags & RC_DIAG_HSV_NOFMA) ? 0 : 1;
+    if (which == 0) rc_launch_vector_color(c, d_flow, d_step, w, h, d_img, d_istep, prev, next, fma);
+    else rc_launch_shear_color(c, d_flow, d_step, w, h, d_img, d_istep, prev, next, fma);
+    CHECK_LAUNCH(c);
+    CUDA_TRY(c, cudaMemcpyAsync(prev, next, 4, cudaMemcpyDeviceToDevice, c->stream));     // `static max = max_new;`
+    if (himg) CUDA_TRY(c, cudaMemcpy2DAsync(img, img_step, d_img, d_istep, (size_t)w * 3, h, cudaMemcpyDeviceToHost, c->stream));
+    if (max_io) CUDA_TRY(c, cudaMemcpyAsync(max_io, prev, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (himg || max_io) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return RC_OK;
+}
+
+int rc_vector_to_color(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, uint8_t* bgr, size_t bgr_step,
+                       float* max_displacement, int flags)
+{
+    return color_impl(c, 0, flow, flow_step, w, h, bgr, bgr_step, max_displacement, flags);
+}
+
+int rc_shear_rate_to_color(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, uint8_t* img, size_t img_step,
+                           float* max_frobenius, int flags)
+{
+    return color_impl(c, 1, flow, flow_step, w, h, img, img_step, max_frobenius, flags);
 }
 
 // ---- fused per-frame / per-batch step -------------------------------------------------------------------------

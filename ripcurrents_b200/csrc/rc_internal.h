@@ -19,7 +19,7 @@
 // kernel classes for rc_profile_* (per-launch CUDA-event timing) -- order matches rc_kernel_names[]
 enum RcKernelId { K_RESERVED = 0, K_PYR_V, K_POLYEXP, K_UPDATE_MATRICES, K_FLOW_ITER_FUSED, K_FLOW_ITER_FINAL,
                   K_FLOW_LAYER, K_POLAR_HIST, K_THRESHOLDS, K_CLASSIFY, K_WINDOW, K_ADVECT, K_STREAKLINE, K_MISC,
-                  K_FIELDS, K_COUNT };
+                  K_FIELDS, K_DIAG, K_COUNT };
 extern const char* const rc_kernel_names[K_COUNT];
 
 struct PolyCoef {          // polynomial-expansion kernels; entries beyond n are zero
@@ -129,6 +129,9 @@ struct rc_ctx {
     // generic scratch for host-pointer arguments
     void* d_tmp = nullptr;  size_t d_tmp_cap = 0;
     void* d_tmp2 = nullptr; size_t d_tmp2_cap = 0;
+    // diagnostics state (diag.cu): [0] vectorToColor max of the previous call, [1] its new max (bits), [2]/[3] the same
+    // for shearRateToColor, [4] meanval; fp64 partial sums from byte 64 on.  The reference keeps these in function statics.
+    float* d_diag = nullptr;
 
     // aggregation state
     unsigned long long* d_hist2d = nullptr;   // cumulative counters, RC_HIST_CELLS
@@ -215,6 +218,14 @@ void rc_launch_fields(rc_ctx* c, const float* field, const float* src0, const fl
                       float* mag_out, float* ratio_out, uint8_t* const gray[3], uint8_t* const bgr[3], unsigned* d_maxenc,
                       double* d_max);
 void rc_launch_positions(rc_ctx* c, const float* field, int w, int h, float* density, int zero_first);
+
+// ---- diag.cu ---------------------------------------------------------------------------------------
+void rc_launch_sub_mean_magnitude(rc_ctx* c, float* flow, size_t step, int w, int h, int sequential, double* d_partial,
+                                  float* d_meanval);
+void rc_launch_vector_color(rc_ctx* c, const float* flow, size_t step, int w, int h, uint8_t* bgr, size_t bstep,
+                            const float* d_prev_max, unsigned* d_new_max, int fma);
+void rc_launch_shear_color(rc_ctx* c, const float* flow, size_t step, int w, int h, uint8_t* img, size_t istep,
+                           const float* d_prev_max, unsigned* d_new_max, int fma);
 
 // ---- advect.cu -------------------------------------------------------------------------------------
 void rc_launch_advect(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float* seeds, size_t n, float dt,

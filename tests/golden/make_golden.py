@@ -85,7 +85,23 @@ def fields():
     np.savez_compressed(os.path.join(HERE, "fields.npz"), cv2_version=np.array(cv2.__version__), **out)
 
 
+def diag():
+    # 8-bit HSV -> BGR (cvtColor, used by vectorToColor / shearRateToColor): the S = 255 plane both functions produce,
+    # plus random triples; rows are multiples of 32 pixels (cv2 rounds the last width % 32 pixels of a row differently)
+    hh, vv = np.meshgrid(np.arange(192), np.arange(0, 256, 2), indexing="ij")
+    plane = np.stack([hh, np.full_like(hh, 255), vv], -1).astype(np.uint8)
+    rng = np.random.default_rng(13)
+    rnd = rng.integers(0, 256, (32, 256, 3), dtype=np.uint8)
+    out = {"plane_hsv": plane, "plane_bgr": cv2.cvtColor(plane, cv2.COLOR_HSV2BGR),
+           "rnd_hsv": rnd, "rnd_bgr": cv2.cvtColor(rnd, cv2.COLOR_HSV2BGR)}
+    cv2.setUseOptimized(False)
+    out["rnd_bgr_noopt"] = cv2.cvtColor(rnd, cv2.COLOR_HSV2BGR)
+    cv2.setUseOptimized(True)
+    np.savez_compressed(os.path.join(HERE, "hsv2bgr.npz"), cv2_version=np.array(cv2.__version__), **out)
+
+
 if __name__ == "__main__":
     main()
     ingest()
     fields()
+    diag()

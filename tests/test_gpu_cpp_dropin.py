@@ -18,7 +18,7 @@ def test_cpp_frame_loop_matches_oracle(tmp_path, oracle):
     raw = tmp_path / "frames.raw"; out = tmp_path / "out.bin"
     fr.tofile(raw)
     subprocess.check_call([demo, str(raw), str(w), str(h), str(n), str(out)], timeout=300)
-    rec = np.fromfile(out, np.float32).reshape(n - 1, 10)
+    rec = np.fromfile(out, np.float32).reshape(n - 1, 13)
 
     ctx = Context(0)
     P = (0.5, 2, 3, 2, 15, 1.2, 0)
@@ -30,6 +30,7 @@ def test_cpp_frame_loop_matches_oracle(tmp_path, oracle):
     cap = n + 1
     verts = np.zeros((2, cap, 2), np.float32); cnt = np.ones(2, np.int32); verts[:, 0] = em
     upper = np.float32(100.0)
+    vmax = smax = 0.0; simg = np.zeros((h, w, 3), np.uint8)
     for i in range(1, n):
         flow = ctx.farneback(fr[i - 1], fr[i], *P).copy()
         oracle.advect(flow, disp, 2.0, 1, float(upper), oracle.ADV_FIELD, dist=dist)
@@ -52,4 +53,12 @@ def test_cpp_frame_loop_matches_oracle(tmp_path, oracle):
         for k, img in enumerate(fields):
             assert rec[i - 1, 6 + k] == np.float32((img.astype(np.float64) * [1, 2, 3]).sum()), (i, k)
         assert rec[i - 1, 9] == np.float32(dens[..., 2].astype(np.float64).sum()), i
+        # flow diagnostics (module:900-1138); the statics start at 0 and carry the previous frame's maxima
+        _, vimg, vmax = oracle.vector_to_color(flow, vmax)
+        smax = oracle.shear_to_color(flow, simg, smax)
+        centred = flow.copy(); oracle.subtract_mean_magnitude(centred)
+        w123 = np.array([1, 2, 3])
+        assert rec[i - 1, 10] == np.float32((vimg.astype(np.float64) * w123).sum()), i
+        assert rec[i - 1, 11] == np.float32((simg.astype(np.float64) * w123).sum()), i
+        assert rec[i - 1, 12] == np.float32((centred[..., 0].astype(np.float64) + 2.0 * centred[..., 1]).sum()), i
     ctx.close()

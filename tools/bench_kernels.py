@@ -84,6 +84,16 @@ def main():
         c.h, vp(pf), vp(pd), C.c_int(w), C.c_int(h), C.c_int(0), vp(sf), vp(imgs[0]), vp(imgs[1]), vp(imgs[2]), vp(dens), None))),
         1, "frames")
 
+    # ---- diagnostics on the resident 1080p flow (device pointers, state kept in the context)
+    dflow = torch.randn((h, w, 2), device=dev)
+    dimg = torch.zeros((h, w, 3), dtype=torch.uint8, device=dev)
+    emit("vector_to_color_1080p", timed(c, lambda: c._chk(c.lib.rc_vector_to_color(
+        c.h, vp(dflow), C.c_size_t(w * 8), C.c_int(w), C.c_int(h), vp(dimg), C.c_size_t(w * 3), None, C.c_int(0)))), 1, "frames")
+    emit("shear_rate_to_color_1080p", timed(c, lambda: c._chk(c.lib.rc_shear_rate_to_color(
+        c.h, vp(dflow), C.c_size_t(w * 8), C.c_int(w), C.c_int(h), vp(dimg), C.c_size_t(w * 3), None, C.c_int(0)))), 1, "frames")
+    emit("subtract_mean_magnitude_1080p", timed(c, lambda: c._chk(c.lib.rc_subtract_mean_magnitude(
+        c.h, vp(dflow), C.c_size_t(w * 8), C.c_int(w), C.c_int(h), C.c_int(0), None))), 1, "frames")
+
     # ---- ingest and mask clean-up
     bgr = torch.randint(0, 256, (8, 1080, 1920, 3), dtype=torch.uint8, device=dev)
     gray = torch.empty((8, 480, 640), dtype=torch.uint8, device=dev)
