@@ -1067,6 +1067,168 @@ flow_layer_kernel(FlowArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// FAST path, windows of half-width M = 2, 5, 10 (winsize 5 of the Android fork, 10 of main.cpp:1119,1481, 20/21 of
+// main.cpp:609,961 and of the 4K configuration): one updateFlow iteration per launch, MARCHING formulation.
+// A CTA owns a strip of TX = 64 columns and walks down a segment of rows in steps of RB = 16:
+//   stage   RB rows of the five M planes (TX + 2M columns, replicate-clamped) into shared memory  -- every load of
+//           the step is issued before any is consumed;
+//   h-blur  thread = 4 adjacent pixels of one (row, channel): 16-byte shared loads, result into a ring of RB + 2M
+//           horizontally blurred rows;
+//   v-blur  thread = (column, 4 rows): its 4 + 2M ring values per channel are read once into registers, the five sums
+//           of its four pixels stay in registers for the fp32 solve, then the fused updateMatrices (-> M of the next
+//           iteration) or the flow store (+ the frame's direction/speed histogram on layer 0).
+// Compared with square tiles nothing is recomputed vertically (2M warm-up rows per segment instead of 2M per 16 rows),
+// all 256 threads work in every phase, and there are two barriers per 16 rows.  Box windows use running sums.
+// ---------------------------------------------------------------------------------------------------
+template <int M, bool FUSE, bool BOX>
+__global__ void __launch_bounds__(256, 2)
+flow_march_kernel(FlowArgs a, int mi, int SEG)
+{
+    constexpr int TX = 64, RB = 16, WP = TX + 2 * M, WPA = (WP + 3) & ~3, RING = RB + 2 * M;
+    extern __shared__ __align__(16) float msm[];
+    float* sRaw = msm;                         // [RB][5][WPA]
+    float* sRing = msm + RB * 5 * WPA;         // [RING][5][TX]
+    __shared__ unsigned int sH[FUSE ? 1 : RC_HIST_CELLS];
+    __shared__ unsigned short sKeys[FUSE ? 1 : 256];
+    __shared__ int sNKeys;
+    const int w = a.w, h = a.h, j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int x0 = blockIdx.y * TX, y0 = blockIdx.z * SEG;
+    const float* Min = a.M + (size_t)j * a.m_stride + (size_t)mi * 5 * a.plane;
+    const bool do_hist = !FUSE && a.hist_delta != nullptr;
+    if (do_hist) {
+        for (int i = tid; i < RC_HIST_CELLS; i += 256) sH[i] = 0;
+        if (tid == 0) sNKeys = 0;
+    }
+    float kk[M + 1];
+#pragma unroll
+    for (int i = 0; i <= M; i++) kk[i] = a.win.k[i];
+    const float ps = a.win.post_scale;
+    const RView R0 = rview(a.R0(j), a.plane), R1 = rview(a.R1(j), a.plane);
+    const int nout = min(SEG, h - y0), total = nout + 2 * M;          // staged row s <-> image row y0 - M + s (clamped)
+    const int col = tid & 63, rbk = tid >> 6;                          // v-blur role
+    int ns = 0, no = 0;
+    while (ns < total) {
+        const int cnt = min(RB, total - ns);
+        // ---- stage: warp per (row, channel)
+        for (int rc = wrp; rc < cnt * 5; rc += 8) {
+            const int r = rc / 5, c = rc - 5 * r;
+            const float* grow = Min + (size_t)c * a.plane + (size_t)clampi(y0 - M + ns + r, 0, h - 1) * a.pitch;
+            float* dst = sRaw + (r * 5 + c) * WPA;
+#pragma unroll
+            for (int q = 0; q < (WP + 31) / 32; q++) {
+                const int rx = lane + 32 * q;
+                if (rx < WP) dst[rx] = __ldg(grow + clampi(x0 - M + rx, 0, w - 1));
+            }
+        }
+        __syncthreads();
+        // ---- horizontal blur: item = (row, channel, group of 4 pixels)
+        for (int it = tid; it < cnt * 5 * (TX / 4); it += 256) {
+            const int xg = it & 15, rc = it >> 4;
+            const int r = rc / 5, c = rc - 5 * r;
+            float win[4 + 2 * M + 3];
+#pragma unroll
+            for (int q = 0; q < (4 + 2 * M + 3) / 4; q++)
+                *reinterpret_cast<float4*>(win + 4 * q) = *reinterpret_cast<const float4*>(sRaw + rc * WPA + 4 * xg + 4 * q);
+            float o[4];
+            if (BOX) {
+                float run = win[0];
+#pragma unroll
+                for (int i = 1; i <= 2 * M; i++) run += win[i];
+                o[0] = run;
+#pragma unroll
+                for (int i = 1; i < 4; i++) { run += win[i + 2 * M] - win[i - 1]; o[i] = run; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float v = win[i + M] * kk[0];
+#pragma unroll
+                    for (int k = 1; k <= M; k++) v = fmaf(win[i + M + k] + win[i + M - k], kk[k], v);
+                    o[i] = v;
+                }
+            }
+            *reinterpret_cast<float4*>(sRing + (((ns + r) % RING) * 5 + c) * TX + 4 * xg) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        __syncthreads();
+        ns += cnt;
+        // ---- vertical blur + solve for the output rows whose window is complete: no .. min(ns - 2M, nout) - 1
+        const int lim = min(ns - 2 * M, nout);
+        const int o0 = no + 4 * rbk;                                    // this thread's rows o0 .. o0 + 3 (local)
+        if (o0 < lim) {
+            float s[4][5];
+            int slot0 = o0 % RING;
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                float win[4 + 2 * M];
+                int sl = slot0;
+#pragma unroll
+                for (int i = 0; i < 4 + 2 * M; i++) {
+                    win[i] = sRing[(sl * 5 + c) * TX + col];
+                    sl = sl + 1 == RING ? 0 : sl + 1;
+                }
+                if (BOX) {
+                    float run = win[0];
+#pragma unroll
+                    for (int i = 1; i <= 2 * M; i++) run += win[i];
+                    s[0][c] = run * ps;
+#pragma unroll
+                    for (int i = 1; i < 4; i++) { run += win[i + 2 * M] - win[i - 1]; s[i][c] = run * ps; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        float v = win[i + M] * kk[0];
+#pragma unroll
+                        for (int k = 1; k <= M; k++) v = fmaf(win[i + M + k] + win[i + M - k], kk[k], v);
+                        s[i][c] = v * ps;
+                    }
+                }
+            }
+            const int x = x0 + col;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int y = y0 + o0 + i;
+                const bool in = x < w && o0 + i < lim;
+                float2 f = make_float2(0.f, 0.f);
+                if (in) f = solve_fast(s[i][0], s[i][1], s[i][2], s[i][3], s[i][4]);
+                if (FUSE) {
+                    if (in) {
+                        float mm[5];
+                        update_matrices_core<false>(x, y, f.x, f.y, w, h, R0, R1, a.pitch, mm);
+                        float* Mo = a.M + (size_t)j * a.m_stride + (size_t)(mi ^ 1) * 5 * a.plane;
+                        const size_t o = (size_t)y * a.pitch + x;
+#pragma unroll
+                        for (int c = 0; c < 5; c++) Mo[c * a.plane + o] = mm[c];
+                    }
+                } else {
+                    if (in) reinterpret_cast<float2*>(a.out(j))[(size_t)y * w + x] = f;
+                    if (do_hist) {
+                        const int key = in ? hist_key_fast(f.x, f.y) : -1;
+                        const unsigned peers = __match_any_sync(0xffffffffu, key);
+                        if (key >= 0 && (int)(__ffs(peers) - 1) == lane) {
+                            if (atomicAdd(&sH[key], __popc(peers)) == 0) {
+                                const int slot = atomicAdd(&sNKeys, 1);
+                                if (slot < 256) sKeys[slot] = (unsigned short)key;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        no = max(lim, 0);
+    }
+    if (do_hist) {
+        __syncthreads();
+        unsigned int* dst = a.hist_delta + (size_t)j * RC_HIST_CELLS;
+        const int nk = sNKeys;
+        if (nk <= 256) {
+            if (tid < nk) { const int k = sKeys[tid]; atomicAdd(&dst[k], sH[k]); }
+        } else {
+            for (int i = tid; i < RC_HIST_CELLS; i += 256)
+                if (sH[i]) atomicAdd(&dst[i], sH[i]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // FAST path, 3x3 window, register/shuffle formulation of the same fused layer: a WARP owns a 32-column strip
 // (32 - 2*NT useful columns) and marches down a segment of rows.  Lane = column.  The last two rows of M of every
 // iteration level live in registers; the vertical 3-sum is formed from them, the horizontal one with two shuffles
@@ -1450,6 +1612,27 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         dim3 gt(nb, (L.w + 63) / 64, (L.h + 15) / 16);
         const bool box = !c->win.gaussian;
         const bool spec = tiled && (m == 2 || m == 5 || m == 10);
+        // marching formulation (default) or the square-tile one (RC_FLOW_LARGE=tiled), DESIGN.md section 7
+        static const bool use_march = !(getenv("RC_FLOW_LARGE") && !strcmp(getenv("RC_FLOW_LARGE"), "tiled"));
+        static const int march_seg_env = getenv("RC_MARCH_SEG") ? atoi(getenv("RC_MARCH_SEG")) : 0;
+        const int mnseg = (L.h + 127) / 128;
+        const int MSEG = march_seg_env > 0 ? march_seg_env : ((L.h + mnseg - 1) / mnseg + 3) & ~3;
+        dim3 gm(nb, (L.w + 63) / 64, (L.h + MSEG - 1) / MSEG);
+        const size_t msm = sizeof(float) * (16 * 5 * (size_t)((64 + 2 * m + 3) & ~3) + (size_t)(16 + 2 * m) * 5 * 64);
+        if (spec && use_march) {
+            static bool configured[64] = {false};
+            if (!configured[c->device & 63]) {
+                const int big = (int)(sizeof(float) * (16 * 5 * 84 + 36 * 5 * 64));
+#define RC_CFG(MM) \
+    cudaFuncSetAttribute(flow_march_kernel<MM, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
+    cudaFuncSetAttribute(flow_march_kernel<MM, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
+    cudaFuncSetAttribute(flow_march_kernel<MM, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
+    cudaFuncSetAttribute(flow_march_kernel<MM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)
+                RC_CFG(2); RC_CFG(5); RC_CFG(10);
+#undef RC_CFG
+                configured[c->device & 63] = true;
+            }
+        }
         bool hist_fused = false;
         int mi = 0;
         for (int it = 0; it < T; it++) {
@@ -1457,7 +1640,10 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
                 KScope ks(c, K_FLOW_ITER_FUSED, 80.0 * npx);
                 if (spec) {
 #define RC_LAUNCH_M(MM, FU) \
-    do { if (box) flow_iter_tiled_m_kernel<MM, FU, true><<<gt, 256, 0, c->stream>>>(a, mi); \
+    do { if (use_march) { \
+             if (box) flow_march_kernel<MM, FU, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
+             else flow_march_kernel<MM, FU, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
+         } else if (box) flow_iter_tiled_m_kernel<MM, FU, true><<<gt, 256, 0, c->stream>>>(a, mi); \
          else flow_iter_tiled_m_kernel<MM, FU, false><<<gt, 256, 0, c->stream>>>(a, mi); } while (0)
                     if (m == 2) RC_LAUNCH_M(2, true); else if (m == 5) RC_LAUNCH_M(5, true); else RC_LAUNCH_M(10, true);
                 } else if (tiled) flow_iter_tiled_kernel<true><<<gt, 256, tsm, c->stream>>>(a, mi);
