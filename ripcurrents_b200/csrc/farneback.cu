@@ -18,6 +18,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include "rc_internal.h"
+#include <cuda_pipeline.h>
 
 namespace {
 
@@ -1080,8 +1081,11 @@ flow_layer_kernel(FlowArgs a)
 // Compared with square tiles nothing is recomputed vertically (2M warm-up rows per segment instead of 2M per 16 rows),
 // all 256 threads work in every phase, and there are two barriers per 16 rows.  Box windows use running sums.
 // ---------------------------------------------------------------------------------------------------
-template <int M, bool FUSE, bool BOX>
-__global__ void __launch_bounds__(256, 2)
+// FIRST: the first iteration of a layer.  M does not exist yet: the staged rows are COMPUTED (flow initialisation from
+// the coarser layer + updateMatrices, at the replicate-clamped pixel) instead of copied, which removes the separate
+// updateMatrices launch and its 20 B/px write + 20 B/px read.
+template <int M, bool FUSE, bool BOX, bool FIRST>
+__global__ void __launch_bounds__(256, FUSE ? 3 : 2)
 flow_march_kernel(FlowArgs a, int mi, int SEG)
 {
     constexpr int TX = 64, RB = 16, WP = TX + 2 * M, WPA = (WP + 3) & ~3, RING = RB + 2 * M;
@@ -1107,19 +1111,54 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
     const int nout = min(SEG, h - y0), total = nout + 2 * M;          // staged row s <-> image row y0 - M + s (clamped)
     const int col = tid & 63, rbk = tid >> 6;                          // v-blur role
     int ns = 0, no = 0;
+    // stage: warp per (row, channel); asynchronous copies (global -> shared without registers), so the rows of step b+1
+    // are in flight while step b is blurred vertically and solved
+    const float2* coarse = FIRST && a.coarse ? reinterpret_cast<const float2*>(a.coarse + (size_t)j * a.coarse_stride) : nullptr;
+    auto stage = [&](int first, int cnt) {
+        if constexpr (FIRST) {
+            constexpr int NQ = (WP + 31) / 32;
+            int xs[NQ], csx[NQ]; float cfx[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                xs[q] = clampi(x0 - M + lane + 32 * q, 0, w - 1);
+                csx[q] = 0; cfx[q] = 0.f;
+                if (coarse) resize_coef(xs[q], a.cw, a.sxs, csx[q], cfx[q]);
+            }
+            for (int r = wrp; r < cnt; r += 8) {
+                const int y = clampi(y0 - M + first + r, 0, h - 1);
+                int csy = 0; float cfy = 0.f;
+                if (coarse) resize_coef(y, a.ch, a.sys, csy, cfy);
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    const int rx = lane + 32 * q;
+                    if (rx < WP) {
+                        float2 fi = make_float2(0.f, 0.f);
+                        if (coarse) fi = upsample_flow_tab(coarse, a.cw, a.ch, csx[q], cfx[q], csy, cfy, a.fscale);
+                        float mm[5];
+                        update_matrices_core<false>(xs[q], y, fi.x, fi.y, w, h, R0, R1, a.pitch, mm);
+#pragma unroll
+                        for (int c = 0; c < 5; c++) sRaw[(r * 5 + c) * WPA + rx] = mm[c];
+                    }
+                }
+            }
+        } else {
+            for (int rc = wrp; rc < cnt * 5; rc += 8) {
+                const int r = rc / 5, c = rc - 5 * r;
+                const float* grow = Min + (size_t)c * a.plane + (size_t)clampi(y0 - M + first + r, 0, h - 1) * a.pitch;
+                float* dst = sRaw + (r * 5 + c) * WPA;
+#pragma unroll
+                for (int q = 0; q < (WP + 31) / 32; q++) {
+                    const int rx = lane + 32 * q;
+                    if (rx < WP) __pipeline_memcpy_async(dst + rx, grow + clampi(x0 - M + rx, 0, w - 1), 4);
+                }
+            }
+            __pipeline_commit();
+        }
+    };
+    if (!FIRST) stage(0, min(RB, total));
     while (ns < total) {
         const int cnt = min(RB, total - ns);
-        // ---- stage: warp per (row, channel)
-        for (int rc = wrp; rc < cnt * 5; rc += 8) {
-            const int r = rc / 5, c = rc - 5 * r;
-            const float* grow = Min + (size_t)c * a.plane + (size_t)clampi(y0 - M + ns + r, 0, h - 1) * a.pitch;
-            float* dst = sRaw + (r * 5 + c) * WPA;
-#pragma unroll
-            for (int q = 0; q < (WP + 31) / 32; q++) {
-                const int rx = lane + 32 * q;
-                if (rx < WP) dst[rx] = __ldg(grow + clampi(x0 - M + rx, 0, w - 1));
-            }
-        }
+        if (FIRST) stage(ns, cnt); else __pipeline_wait_prior(0);
         __syncthreads();
         // ---- horizontal blur: item = (row, channel, group of 4 pixels)
         for (int it = tid; it < cnt * 5 * (TX / 4); it += 256) {
@@ -1150,6 +1189,7 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
         }
         __syncthreads();
         ns += cnt;
+        if (!FIRST && ns < total) stage(ns, min(RB, total - ns));
         // ---- vertical blur + solve for the output rows whose window is complete: no .. min(ns - 2M, nout) - 1
         const int lim = min(ns - 2 * M, nout);
         const int o0 = no + 4 * rbk;                                    // this thread's rows o0 .. o0 + 3 (local)
@@ -1594,12 +1634,14 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         }
         dim3 b(32, 8), g((L.w + 31) / 32, (L.h + 7) / 8, nb);
         const bool tiled = !c->strict && c->win.m >= 1 && c->win.m <= 16;
-        {
+        const int m = c->win.m;
+        const bool march = tiled && (m == 2 || m == 5 || m == 10) &&
+                           !(getenv("RC_FLOW_LARGE") && !strcmp(getenv("RC_FLOW_LARGE"), "tiled"));
+        if (!march) {      // the marching kernel computes M inside its first iteration
             KScope ks(c, K_UPDATE_MATRICES, (a.coarse ? 62.0 : 60.0) * npx);
             if (c->strict) update_matrices_kernel<true><<<g, b, 0, c->stream>>>(a, 0);
             else update_matrices_kernel<false><<<g, b, 0, c->stream>>>(a, 0);
         }
-        const int m = c->win.m;
         const size_t tsm = sizeof(float) * ((size_t)(16 + 2 * m) * (64 + 2 * m) + 16 * (size_t)(64 + 2 * m));
         if (tiled && tsm > 48 * 1024) {
             static size_t configured[64] = {0};   // per device
@@ -1613,7 +1655,7 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         const bool box = !c->win.gaussian;
         const bool spec = tiled && (m == 2 || m == 5 || m == 10);
         // marching formulation (default) or the square-tile one (RC_FLOW_LARGE=tiled), DESIGN.md section 7
-        static const bool use_march = !(getenv("RC_FLOW_LARGE") && !strcmp(getenv("RC_FLOW_LARGE"), "tiled"));
+        const bool use_march = march;
         static const int march_seg_env = getenv("RC_MARCH_SEG") ? atoi(getenv("RC_MARCH_SEG")) : 0;
         const int mnseg = (L.h + 127) / 128;
         const int MSEG = march_seg_env > 0 ? march_seg_env : ((L.h + mnseg - 1) / mnseg + 3) & ~3;
@@ -1623,26 +1665,30 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
             static bool configured[64] = {false};
             if (!configured[c->device & 63]) {
                 const int big = (int)(sizeof(float) * (16 * 5 * 84 + 36 * 5 * 64));
-#define RC_CFG(MM) \
-    cudaFuncSetAttribute(flow_march_kernel<MM, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
-    cudaFuncSetAttribute(flow_march_kernel<MM, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
-    cudaFuncSetAttribute(flow_march_kernel<MM, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
-    cudaFuncSetAttribute(flow_march_kernel<MM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)
+#define RC_CFG1(MM, FU, BX) \
+    cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
+    cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)
+#define RC_CFG(MM) RC_CFG1(MM, true, true); RC_CFG1(MM, true, false); RC_CFG1(MM, false, true); RC_CFG1(MM, false, false)
                 RC_CFG(2); RC_CFG(5); RC_CFG(10);
 #undef RC_CFG
+#undef RC_CFG1
                 configured[c->device & 63] = true;
             }
         }
         bool hist_fused = false;
         int mi = 0;
         for (int it = 0; it < T; it++) {
+            const double first_extra = use_march && it == 0 ? (a.coarse ? 22.0 : 20.0) : 0.0;   // R0 + R1 (+ coarse flow) instead of M
             if (it < T - 1) {
-                KScope ks(c, K_FLOW_ITER_FUSED, 80.0 * npx);
+                KScope ks(c, K_FLOW_ITER_FUSED, (80.0 + first_extra) * npx);
                 if (spec) {
 #define RC_LAUNCH_M(MM, FU) \
     do { if (use_march) { \
-             if (box) flow_march_kernel<MM, FU, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
-             else flow_march_kernel<MM, FU, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
+             if (it == 0) { \
+                 if (box) flow_march_kernel<MM, FU, true, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
+                 else flow_march_kernel<MM, FU, false, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
+             } else if (box) flow_march_kernel<MM, FU, true, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
+             else flow_march_kernel<MM, FU, false, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
          } else if (box) flow_iter_tiled_m_kernel<MM, FU, true><<<gt, 256, 0, c->stream>>>(a, mi); \
          else flow_iter_tiled_m_kernel<MM, FU, false><<<gt, 256, 0, c->stream>>>(a, mi); } while (0)
                     if (m == 2) RC_LAUNCH_M(2, true); else if (m == 5) RC_LAUNCH_M(5, true); else RC_LAUNCH_M(10, true);
@@ -1650,7 +1696,7 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
                 else update_flow_strict_kernel<true><<<g, b, 0, c->stream>>>(a, mi);
                 mi ^= 1;
             } else {
-                KScope ks(c, K_FLOW_ITER_FINAL, 28.0 * npx);
+                KScope ks(c, K_FLOW_ITER_FINAL, (28.0 + first_extra) * npx);
                 if (spec) {
                     if (m == 2) RC_LAUNCH_M(2, false); else if (m == 5) RC_LAUNCH_M(5, false); else RC_LAUNCH_M(10, false);
                     hist_fused = true;
