@@ -785,137 +785,6 @@ flow_iter_tiled_kernel(FlowArgs a, int mi)
 
 __device__ __forceinline__ int hist_key_fast(float dx, float dy);   // aggregate.cu twin, defined below
 
-// Register-blocked specialisation of flow_iter_tiled_kernel for the window half-widths the reference uses
-// (M = 2: winsize 5 of the Android fork; M = 5: winsize 10 of main.cpp:1119,1481; M = 10: winsize 20/21 of
-// main.cpp:609,961 and of the 4K configuration).  Same 64x16 tile and channel-at-a-time staging, but
-//   vertical pass  : thread = (column, 8-row half): its 8 + 2M inputs are read once into registers;
-//   horizontal pass: thread = 4 adjacent pixels: its 4 + 2M inputs come from 16-byte shared loads;
-//   box windows use running sums (one add + one subtract per output instead of 2M+1 taps).
-// The frame's direction/speed histogram is fused into the final iteration of layer 0.
-template <int M, bool FUSE, bool BOX>
-__global__ void __launch_bounds__(256)
-flow_iter_tiled_m_kernel(FlowArgs a, int mi)
-{
-    constexpr int TX = 64, TY = 16, WP = TX + 2 * M, HP = TY + 2 * M, WPA = (WP + 3) & ~3;
-    __shared__ __align__(16) float sIn[HP * WP];
-    __shared__ __align__(16) float sV[TY * WPA];
-    __shared__ unsigned int sH[FUSE ? 1 : RC_HIST_CELLS];
-    __shared__ unsigned short sKeys[FUSE ? 1 : 256];
-    __shared__ int sNKeys;
-    const int w = a.w, h = a.h, j = blockIdx.x, tid = threadIdx.x;       // grid = (pairs, tiles_x, tiles_y)
-    const int x0 = blockIdx.y * TX, y0 = blockIdx.z * TY;
-    const float* Min = a.M + (size_t)j * a.m_stride + (size_t)mi * 5 * a.plane;
-    const int lane = tid & 31, wrp = tid >> 5;
-    const int row = tid >> 4, xg = tid & 15;            // horizontal-pass role: pixels (4*xg .. 4*xg+3, row)
-    const bool do_hist = !FUSE && a.hist_delta != nullptr;
-    if (!FUSE && do_hist) {
-        for (int i = tid; i < RC_HIST_CELLS; i += 256) sH[i] = 0;
-        if (tid == 0) sNKeys = 0;
-    }
-    float kk[M + 1];
-#pragma unroll
-    for (int i = 0; i <= M; i++) kk[i] = a.win.k[i];
-    float s[4][5];
-#pragma unroll
-    for (int c = 0; c < 5; c++) {
-        const float* P = Min + (size_t)c * a.plane;
-        for (int ry = wrp; ry < HP; ry += 8) {
-            const float* grow = P + (size_t)clampi(y0 - M + ry, 0, h - 1) * a.pitch;
-            for (int rx = lane; rx < WP; rx += 32) sIn[ry * WP + rx] = __ldg(grow + clampi(x0 - M + rx, 0, w - 1));
-        }
-        __syncthreads();
-        if (tid < 2 * WP) {
-            const int col = tid < WP ? tid : tid - WP, r0 = tid < WP ? 0 : 8;
-            float win[8 + 2 * M];
-#pragma unroll
-            for (int i = 0; i < 8 + 2 * M; i++) win[i] = sIn[(r0 + i) * WP + col];
-            if (BOX) {
-                float run = win[0];
-#pragma unroll
-                for (int i = 1; i <= 2 * M; i++) run += win[i];
-                sV[r0 * WPA + col] = run;
-#pragma unroll
-                for (int i = 1; i < 8; i++) { run += win[i + 2 * M] - win[i - 1]; sV[(r0 + i) * WPA + col] = run; }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    float v = win[i + M] * kk[0];
-#pragma unroll
-                    for (int k = 1; k <= M; k++) v = fmaf(win[i + M + k] + win[i + M - k], kk[k], v);
-                    sV[(r0 + i) * WPA + col] = v;
-                }
-            }
-        }
-        __syncthreads();
-        {
-            float win[4 + 2 * M + 3];
-            // the window starts at column 4*xg (16-byte aligned); (4 + 2M) values rounded up to whole float4s
-#pragma unroll
-            for (int q = 0; q < (4 + 2 * M + 3) / 4; q++)
-                *reinterpret_cast<float4*>(win + 4 * q) = *reinterpret_cast<const float4*>(sV + row * WPA + 4 * xg + 4 * q);
-            if (BOX) {
-                float run = win[0];
-#pragma unroll
-                for (int i = 1; i <= 2 * M; i++) run += win[i];
-                s[0][c] = run * a.win.post_scale;
-#pragma unroll
-                for (int i = 1; i < 4; i++) { run += win[i + 2 * M] - win[i - 1]; s[i][c] = run * a.win.post_scale; }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    float v = win[i + M] * kk[0];
-#pragma unroll
-                    for (int k = 1; k <= M; k++) v = fmaf(win[i + M + k] + win[i + M - k], kk[k], v);
-                    s[i][c] = v * a.win.post_scale;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    const RView R0 = rview(a.R0(j), a.plane), R1 = rview(a.R1(j), a.plane);
-    const int y = y0 + row;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int x = x0 + 4 * xg + i;
-        const bool in = x < w && y < h;
-        float2 f = make_float2(0.f, 0.f);
-        if (in) f = solve_fast(s[i][0], s[i][1], s[i][2], s[i][3], s[i][4]);
-        if (FUSE) {
-            if (in) {
-                float mm[5];
-                update_matrices_core<false>(x, y, f.x, f.y, w, h, R0, R1, a.pitch, mm);
-                float* Mo = a.M + (size_t)j * a.m_stride + (size_t)(mi ^ 1) * 5 * a.plane;
-                const size_t o = (size_t)y * a.pitch + x;
-#pragma unroll
-                for (int c = 0; c < 5; c++) Mo[c * a.plane + o] = mm[c];
-            }
-        } else {
-            if (in) reinterpret_cast<float2*>(a.out(j))[(size_t)y * w + x] = f;
-            if (do_hist) {
-                const int key = in ? hist_key_fast(f.x, f.y) : -1;
-                const unsigned peers = __match_any_sync(0xffffffffu, key);
-                if (key >= 0 && (int)(__ffs(peers) - 1) == lane) {
-                    if (atomicAdd(&sH[key], __popc(peers)) == 0) {
-                        const int slot = atomicAdd(&sNKeys, 1);
-                        if (slot < 256) sKeys[slot] = (unsigned short)key;
-                    }
-                }
-            }
-        }
-    }
-    if (!FUSE && do_hist) {
-        __syncthreads();
-        unsigned int* dst = a.hist_delta + (size_t)j * RC_HIST_CELLS;
-        const int nk = sNKeys;
-        if (nk <= 256) {
-            if (tid < nk) { const int k = sKeys[tid]; atomicAdd(&dst[k], sH[k]); }
-        } else {
-            for (int i = tid; i < RC_HIST_CELLS; i += 256)
-                if (sH[i]) atomicAdd(&dst[i], sH[i]);
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // FAST path, 3x3 window (winsize 2 or 3): ONE kernel per pyramid layer.  A 32x32 output tile carries a halo of
 // NT pixels; the structure matrices M never leave shared memory:
@@ -1635,8 +1504,7 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         dim3 b(32, 8), g((L.w + 31) / 32, (L.h + 7) / 8, nb);
         const bool tiled = !c->strict && c->win.m >= 1 && c->win.m <= 16;
         const int m = c->win.m;
-        const bool march = tiled && (m == 2 || m == 5 || m == 10) &&
-                           !(getenv("RC_FLOW_LARGE") && !strcmp(getenv("RC_FLOW_LARGE"), "tiled"));
+        const bool march = tiled && (m == 2 || m == 5 || m == 10);
         if (!march) {      // the marching kernel computes M inside its first iteration
             KScope ks(c, K_UPDATE_MATRICES, (a.coarse ? 62.0 : 60.0) * npx);
             if (c->strict) update_matrices_kernel<true><<<g, b, 0, c->stream>>>(a, 0);
@@ -1653,15 +1521,13 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         }
         dim3 gt(nb, (L.w + 63) / 64, (L.h + 15) / 16);
         const bool box = !c->win.gaussian;
-        const bool spec = tiled && (m == 2 || m == 5 || m == 10);
-        // marching formulation (default) or the square-tile one (RC_FLOW_LARGE=tiled), DESIGN.md section 7
-        const bool use_march = march;
+        const bool spec = march;      // marching kernel; other half-widths use the generic square-tile kernel
         static const int march_seg_env = getenv("RC_MARCH_SEG") ? atoi(getenv("RC_MARCH_SEG")) : 0;
         const int mnseg = (L.h + 127) / 128;
         const int MSEG = march_seg_env > 0 ? march_seg_env : ((L.h + mnseg - 1) / mnseg + 3) & ~3;
         dim3 gm(nb, (L.w + 63) / 64, (L.h + MSEG - 1) / MSEG);
         const size_t msm = sizeof(float) * (16 * 5 * (size_t)((64 + 2 * m + 3) & ~3) + (size_t)(16 + 2 * m) * 5 * 64);
-        if (spec && use_march) {
+        if (spec) {
             static bool configured[64] = {false};
             if (!configured[c->device & 63]) {
                 const int big = (int)(sizeof(float) * (16 * 5 * 84 + 36 * 5 * 64));
@@ -1678,19 +1544,16 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         bool hist_fused = false;
         int mi = 0;
         for (int it = 0; it < T; it++) {
-            const double first_extra = use_march && it == 0 ? (a.coarse ? 22.0 : 20.0) : 0.0;   // R0 + R1 (+ coarse flow) instead of M
+            const double first_extra = spec && it == 0 ? (a.coarse ? 22.0 : 20.0) : 0.0;   // R0 + R1 (+ coarse flow) instead of M
             if (it < T - 1) {
                 KScope ks(c, K_FLOW_ITER_FUSED, (80.0 + first_extra) * npx);
                 if (spec) {
 #define RC_LAUNCH_M(MM, FU) \
-    do { if (use_march) { \
-             if (it == 0) { \
-                 if (box) flow_march_kernel<MM, FU, true, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
-                 else flow_march_kernel<MM, FU, false, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
-             } else if (box) flow_march_kernel<MM, FU, true, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
-             else flow_march_kernel<MM, FU, false, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
-         } else if (box) flow_iter_tiled_m_kernel<MM, FU, true><<<gt, 256, 0, c->stream>>>(a, mi); \
-         else flow_iter_tiled_m_kernel<MM, FU, false><<<gt, 256, 0, c->stream>>>(a, mi); } while (0)
+    do { if (it == 0) { \
+             if (box) flow_march_kernel<MM, FU, true, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
+             else flow_march_kernel<MM, FU, false, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
+         } else if (box) flow_march_kernel<MM, FU, true, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
+         else flow_march_kernel<MM, FU, false, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); } while (0)
                     if (m == 2) RC_LAUNCH_M(2, true); else if (m == 5) RC_LAUNCH_M(5, true); else RC_LAUNCH_M(10, true);
                 } else if (tiled) flow_iter_tiled_kernel<true><<<gt, 256, tsm, c->stream>>>(a, mi);
                 else update_flow_strict_kernel<true><<<g, b, 0, c->stream>>>(a, mi);
