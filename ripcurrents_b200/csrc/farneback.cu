@@ -317,6 +317,160 @@ pyr0_kernel(const uint8_t* __restrict__ img, size_t step, size_t fstride, int W,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Layers 0, 1 and 2 of a pyr_scale = 0.5 pyramid in ONE pass over the frame (the reference default: three layers with
+// 3-, 3- and 9-tap presmooth).  A CTA stages a 128x32 pixel tile (+3 halo, REFLECT_101) as fp32 in shared memory once
+// and produces the 128x32, 64x16 and 32x8 pixels of the three layer images from it, so the u8 frame is read once
+// instead of three times and one launch replaces three.  Per-pixel arithmetic (tap order, separately rounded products
+// and sums) is that of pyr0_kernel / pyr_half_kernel / pyr_quarter_kernel: the results are bit-identical.
+// ---------------------------------------------------------------------------------------------------
+struct Pyr3Args {
+    const uint8_t* img; size_t step, fstride; int W, H;
+    float* out[3]; int pitch[3]; size_t ostride[3];
+    float k3a[3], k3b[3];       // presmooth taps of layer 0 and layer 1
+    SmoothCoef k9;              // 9 taps of layer 2
+};
+
+// 12 consecutive floats from a 16-byte aligned shared-memory address (three conflict-free 128-bit loads)
+__device__ __forceinline__ void lds12(const float* p, float w[12])
+{
+    *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(p);
+    *reinterpret_cast<float4*>(w + 4) = *reinterpret_cast<const float4*>(p + 4);
+    *reinterpret_cast<float4*>(w + 8) = *reinterpret_cast<const float4*>(p + 8);
+}
+
+__global__ void __launch_bounds__(256)
+pyr3_kernel(Pyr3Args a)
+{
+    constexpr int TW = 128, TH = 32, SP = 136, SR = TH + 6;       // staged: columns X0-4 .. X0+131, rows Y0-3 .. Y0+34
+    __shared__ __align__(16) float sS[SR * SP];
+    __shared__ float2 sHq[SR * 32];                                  // layer 2: H-blurred pair per (staged row, output column)
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH, W = a.W, H = a.H;
+    const uint8_t* img = a.img + (size_t)blockIdx.z * a.fstride;
+    // ---- stage (sS column c <-> image column X0 - 4 + c)
+    const bool interior = X0 >= 4 && X0 + 132 <= W && Y0 >= 3 && Y0 + TH + 3 <= H;
+    if (interior) {
+        for (int r = wrp; r < SR; r += 8) {
+            const unsigned int* grow = reinterpret_cast<const unsigned int*>(img + (size_t)(Y0 - 3 + r) * a.step + (X0 - 4));
+            float* srow = sS + r * SP;
+            for (int q = lane; q < SP / 4; q += 32) {
+                const unsigned int v = __ldg(grow + q);
+                *reinterpret_cast<float4*>(srow + 4 * q) =
+                    make_float4((float)(v & 0xffu), (float)((v >> 8) & 0xffu), (float)((v >> 16) & 0xffu), (float)(v >> 24));
+            }
+        }
+    } else {
+        for (int r = wrp; r < SR; r += 8) {
+            const uint8_t* grow = img + (size_t)reflect101(Y0 - 3 + r, H) * a.step;
+            float* srow = sS + r * SP;
+            for (int cidx = lane; cidx < SP; cidx += 32) srow[cidx] = (float)grow[reflect101(X0 - 4 + cidx, W)];
+        }
+    }
+    __syncthreads();
+    // ---- layer 2, horizontal pass: columns 4X+1 and 4X+2 of every staged row (window columns 4X-3 .. 4X+6)
+    {
+        float k[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) k[i] = a.k9.k[i];
+        for (int it = tid; it < SR * 32; it += 256) {
+            const int r = it >> 5, X = it & 31;
+            float w12[12];
+            lds12(sS + r * SP + 4 * X, w12);
+            const float* v = w12 + 1;                                // image column X0 + 4X - 3
+            float s0 = __fmul_rn(k[0], v[0]), s1 = __fmul_rn(k[0], v[1]);
+#pragma unroll
+            for (int i = 1; i < 9; i++) { s0 = __fadd_rn(s0, __fmul_rn(k[i], v[i])); s1 = __fadd_rn(s1, __fmul_rn(k[i], v[i + 1])); }
+            sHq[it] = make_float2(s0, s1);
+        }
+    }
+    // ---- layer 0: 4 adjacent pixels per item
+    {
+        const float k0 = a.k3a[0], k1 = a.k3a[1], k2 = a.k3a[2];
+        float* out = a.out[0] + (size_t)blockIdx.z * a.ostride[0];
+        for (int it = tid; it < TH * (TW / 4); it += 256) {
+            const int y = it >> 5, x4 = (it & 31) * 4;
+            if (X0 + x4 >= W || Y0 + y >= H) continue;
+            float hb[3][4];
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) {
+                float w12[12];
+                lds12(sS + (y + 2 + rr) * SP + x4, w12);
+                const float* v = w12 + 3;                            // image row Y0 + y - 1 + rr, column X0 + x4 - 1
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    hb[rr][i] = __fadd_rn(__fadd_rn(__fmul_rn(k0, v[i]), __fmul_rn(k1, v[i + 1])), __fmul_rn(k2, v[i + 2]));
+            }
+            float4 o;
+            o.x = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[0][0]), __fmul_rn(k1, hb[1][0])), __fmul_rn(k2, hb[2][0]));
+            o.y = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[0][1]), __fmul_rn(k1, hb[1][1])), __fmul_rn(k2, hb[2][1]));
+            o.z = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[0][2]), __fmul_rn(k1, hb[1][2])), __fmul_rn(k2, hb[2][2]));
+            o.w = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[0][3]), __fmul_rn(k1, hb[1][3])), __fmul_rn(k2, hb[2][3]));
+            *reinterpret_cast<float4*>(out + (size_t)(Y0 + y) * a.pitch[0] + X0 + x4) = o;
+        }
+    }
+    // ---- layer 1: 2 adjacent pixels per item (source window 4 rows x 6 columns)
+    {
+        const float k0 = a.k3b[0], k1 = a.k3b[1], k2 = a.k3b[2];
+        float* out = a.out[1] + (size_t)blockIdx.z * a.ostride[1];
+        const int dw = W / 2, dh = H / 2;
+        for (int it = tid; it < (TH / 2) * (TW / 4); it += 256) {
+            const int y = it >> 5, x2 = (it & 31) * 2;                // layer-1 pixel (X0/2 + x2, Y0/2 + y)
+            const int X = X0 / 2 + x2, Y = Y0 / 2 + y;
+            if (X >= dw || Y >= dh) continue;
+            float hb[4][4];
+#pragma unroll
+            for (int rr = 0; rr < 4; rr++) {
+                float w12[12];
+                lds12(sS + (2 * y + 2 + rr) * SP + 2 * x2, w12);
+                const float* v = w12 + 3;                            // image row 2Y - 1 + rr, column 2X - 1
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    hb[rr][i] = __fadd_rn(__fadd_rn(__fmul_rn(k0, v[i]), __fmul_rn(k1, v[i + 1])), __fmul_rn(k2, v[i + 2]));
+            }
+            float r[2];
+#pragma unroll
+            for (int d = 0; d < 2; d++) {
+                float b[2][2];
+#pragma unroll
+                for (int sr = 0; sr < 2; sr++)
+#pragma unroll
+                    for (int sc = 0; sc < 2; sc++) {
+                        const int c = 2 * d + sc;
+                        b[sr][sc] = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[sr][c]), __fmul_rn(k1, hb[sr + 1][c])), __fmul_rn(k2, hb[sr + 2][c]));
+                    }
+                const float top = __fadd_rn(__fmul_rn(b[0][0], 0.5f), __fmul_rn(b[0][1], 0.5f));
+                const float bot = __fadd_rn(__fmul_rn(b[1][0], 0.5f), __fmul_rn(b[1][1], 0.5f));
+                r[d] = __fadd_rn(__fmul_rn(top, 0.5f), __fmul_rn(bot, 0.5f));
+            }
+            *reinterpret_cast<float2*>(out + (size_t)Y * a.pitch[1] + X) = make_float2(r[0], r[1]);
+        }
+    }
+    __syncthreads();
+    // ---- layer 2, vertical pass: one pixel per thread (rows 4Y-3 .. 4Y+6 = staged rows 4y .. 4y+9)
+    {
+        const int y = tid >> 5, X = X0 / 4 + lane, Y = Y0 / 4 + y;
+        if (X < W / 4 && Y < H / 4) {
+            float k[9];
+#pragma unroll
+            for (int i = 0; i < 9; i++) k[i] = a.k9.k[i];
+            const float2* hq = sHq + (4 * y) * 32 + lane;
+            float2 p = hq[0], q = hq[32];
+            float b00 = __fmul_rn(k[0], p.x), b01 = __fmul_rn(k[0], p.y), b10 = __fmul_rn(k[0], q.x), b11 = __fmul_rn(k[0], q.y);
+#pragma unroll
+            for (int jj = 1; jj < 9; jj++) {
+                p = q; q = hq[(jj + 1) * 32];
+                b00 = __fadd_rn(b00, __fmul_rn(k[jj], p.x)); b01 = __fadd_rn(b01, __fmul_rn(k[jj], p.y));
+                b10 = __fadd_rn(b10, __fmul_rn(k[jj], q.x)); b11 = __fadd_rn(b11, __fmul_rn(k[jj], q.y));
+            }
+            const float top = __fadd_rn(__fmul_rn(b00, 0.5f), __fmul_rn(b01, 0.5f));
+            const float bot = __fadd_rn(__fmul_rn(b10, 0.5f), __fmul_rn(b11, 0.5f));
+            float* out = a.out[2] + (size_t)blockIdx.z * a.ostride[2];
+            out[(size_t)Y * a.pitch[2] + X] = __fadd_rn(__fmul_rn(top, 0.5f), __fmul_rn(bot, 0.5f));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Polynomial expansion (Appendix A.3), STRICT tile kernel: vertical pass fp32 -> shared memory,
 // horizontal pass with fp64 accumulators, replicate borders, every tap, no contraction.
 // ---------------------------------------------------------------------------------------------------
@@ -1359,7 +1513,31 @@ static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
 void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, int nb, int first_slot)
 {
     const int W = c->prm.w, H = c->prm.h;
-    for (int k = 0; k < c->nlayers; k++) {
+    int k_first = 0;
+    // layers 0-2 of the default pyramid in one pass over the frame (RC_PYR=separate: one kernel per layer)
+    static const bool pyr_fused = !(getenv("RC_PYR") && !strcmp(getenv("RC_PYR"), "separate"));
+    if (pyr_fused && c->nlayers >= 3 && W % 4 == 0 && H % 4 == 0 && W >= 16 && H >= 16 && step % 4 == 0 && fstride % 4 == 0 &&
+        (reinterpret_cast<size_t>(d_frames) & 3) == 0 && c->layer[0].w == W && c->layer[0].h == H &&
+        c->layer[1].w * 2 == W && c->layer[1].h * 2 == H && c->layer[2].w * 4 == W && c->layer[2].h * 4 == H &&
+        c->layer[0].smooth.ksize == 3 && c->layer[1].smooth.ksize == 3 && c->layer[2].smooth.ksize == 9) {
+        Pyr3Args p;
+        p.img = d_frames; p.step = step; p.fstride = fstride; p.W = W; p.H = H;
+        double bytes = (double)W * H;
+        for (int k = 0; k < 3; k++) {
+            Layer& L = c->layer[k];
+            p.out[k] = L.I; p.pitch[k] = L.pitch; p.ostride[k] = (size_t)L.pitch * L.h;
+            bytes += 4.0 * L.w * L.h;
+        }
+        for (int i = 0; i < 3; i++) { p.k3a[i] = c->layer[0].smooth.k[i]; p.k3b[i] = c->layer[1].smooth.k[i]; }
+        p.k9 = c->layer[2].smooth;
+        {
+            KScope ks(c, K_PYR_V, bytes * nb);
+            pyr3_kernel<<<dim3((W + 127) / 128, (H + 31) / 32, nb), 256, 0, c->stream>>>(p);
+        }
+        for (int k = 0; k < 3; k++) launch_polyexp(c, c->layer[k], nb, first_slot);
+        k_first = 3;
+    }
+    for (int k = k_first; k < c->nlayers; k++) {
         Layer& L = c->layer[k];
         PyrArgs a;
         a.img = d_frames; a.step = step; a.fstride = fstride; a.W = W; a.H = H; a.dw = L.w; a.dh = L.h;

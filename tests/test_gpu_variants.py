@@ -17,3 +17,21 @@ def test_fused_layer_variant(kernel):
     out = subprocess.run([sys.executable, os.path.join(HERE, "variant_check.py")], env=env, capture_output=True, text=True,
                          timeout=600)
     assert out.returncode == 0 and "variant ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_fused_pyramid_equals_per_layer_kernels(tmp_path):
+    """pyr3_kernel (layers 0-2 in one pass over the frame) must reproduce the per-layer kernels bit for bit."""
+    import numpy as np
+    outs = []
+    for mode in ("fused", "separate"):
+        env = dict(os.environ)
+        if mode == "separate":
+            env["RC_PYR"] = "separate"
+        path = str(tmp_path / (mode + ".npz"))
+        out = subprocess.run([sys.executable, os.path.join(HERE, "pyr_dump.py"), path], env=env, capture_output=True, text=True,
+                             timeout=600)
+        assert out.returncode == 0 and "dumped " + mode in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+        outs.append(np.load(path))
+    assert sorted(outs[0].files) == sorted(outs[1].files) and len(outs[0].files) == 5
+    for k in outs[0].files:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
