@@ -1,5 +1,5 @@
 """Writes the flows of a few frame pairs to an .npz (argv[1]); tests/test_gpu_variants.py runs it with and without
-RC_PYR=separate and requires identical bits (the fused three-layer pyramid kernel against the per-layer kernels)."""
+RC_PYR=separate and requires identical bits (fused three-layer pyramid kernel against the per-layer kernels)."""
 import os
 import sys
 
@@ -16,4 +16,4 @@ for w, h, P in [(1920, 1080, (0.5, 2, 3, 2, 15, 1.2, 0)), (320, 240, (0.5, 2, 3,
     fr = synth.clip(w, h, 2, seed=w + h)
     out["%dx%d" % (w, h)] = c.farneback(fr[0], fr[1], *P).copy()
 np.savez(sys.argv[1], **out)
-print("dumped", os.environ.get("RC_PYR", "fused"))
+print("dumped")
