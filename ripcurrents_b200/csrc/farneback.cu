@@ -1136,6 +1136,7 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
     int ns = 0, no = 0;
     // stage: warp per (row, channel); asynchronous copies (global -> shared without registers), so the rows of step b+1
     // are in flight while step b is blurred vertically and solved
+    const bool interior_x = x0 - M >= 0 && x0 - M + WP <= w;
     const float2* coarse = FIRST && a.coarse ? reinterpret_cast<const float2*>(a.coarse + (size_t)j * a.coarse_stride) : nullptr;
     auto stage = [&](int first, int cnt) {
         if constexpr (FIRST) {
@@ -1169,10 +1170,18 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
                 const int r = rc / 5, c = rc - 5 * r;
                 const float* grow = Min + (size_t)c * a.plane + (size_t)clampi(y0 - M + first + r, 0, h - 1) * a.pitch;
                 float* dst = sRaw + (r * 5 + c) * WPA;
+                if (M % 2 == 0 && interior_x) {            // no column clamping, 8-byte aligned: half the copies
 #pragma unroll
-                for (int q = 0; q < (WP + 31) / 32; q++) {
-                    const int rx = lane + 32 * q;
-                    if (rx < WP) __pipeline_memcpy_async(dst + rx, grow + clampi(x0 - M + rx, 0, w - 1), 4);
+                    for (int q = 0; q < (WP / 2 + 31) / 32; q++) {
+                        const int rx = lane + 32 * q;
+                        if (rx < WP / 2) __pipeline_memcpy_async(dst + 2 * rx, grow + (x0 - M) + 2 * rx, 8);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < (WP + 31) / 32; q++) {
+                        const int rx = lane + 32 * q;
+                        if (rx < WP) __pipeline_memcpy_async(dst + rx, grow + clampi(x0 - M + rx, 0, w - 1), 4);
+                    }
                 }
             }
             __pipeline_commit();
