@@ -37,9 +37,12 @@ if ROOT not in sys.path:
 W, H = 1920, 1080
 PARAMS = (0.5, 2, 3, 2, 15, 1.2, 0)      # ripcurrents.cpp:215
 WINDOW = 10                               # main.cpp:1084
-FRAMES_PER_STEP = 16                      # = the context's max_batch: one batched launch sequence per step
-CLIP_FRAMES = 17                          # distinct synthetic frames per rank; played 0..16,15..1 (ping-pong, period
-                                          # 32 = two steps) so that consecutive frames always differ by one motion step
+# frames per step = the context's max_batch: one batched launch sequence per step.  Measured on one B200 (pairs/s,
+# device-resident): 8 -> 7.9 k, 16 -> 8.45 k, 32 -> 8.8 k, 64 -> 9.1 k (fewer partial waves per launch); 32 keeps the
+# buffering of a live stream at about one second.  RC_BENCH_BATCH overrides it (<= 64).
+FRAMES_PER_STEP = int(os.environ.get("RC_BENCH_BATCH", "32"))
+CLIP_FRAMES = FRAMES_PER_STEP + 1         # distinct synthetic frames per rank, played 0..B,B-1..1 (ping-pong, period 2B =
+                                          # two steps) so that consecutive frames always differ by one motion step
 METRIC = "1080p Farneback flow+aggregation frame pairs/s"
 UNIT = "pairs/s"
 
@@ -246,7 +249,7 @@ def run_ours(args, rank, world, local_rank):
 
     # synthetic clip for this rank's camera stream
     frames = synth.clip(W, H, CLIP_FRAMES, seed=rank)
-    order = list(range(CLIP_FRAMES)) + list(range(CLIP_FRAMES - 2, 0, -1))          # 32 frames = 2 steps
+    order = list(range(CLIP_FRAMES)) + list(range(CLIP_FRAMES - 2, 0, -1))          # 2B frames = 2 steps
     assert len(order) == 2 * FRAMES_PER_STEP
     seq = np.stack([frames[i] for i in order])
     h_seq = torch.from_numpy(seq).pin_memory()                                       # [32, H, W] u8, pinned host
@@ -400,7 +403,7 @@ def run_ours(args, rank, world, local_rank):
                 "config": config_dict(world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": FRAMES_PER_STEP * W * H,
                         "d2h_bytes_per_step": FRAMES_PER_STEP * (W * H + 320), "ms_per_step": ms_e2e / args.steps,
-                        "api": "rc_submit_frames(16 pinned host frames) -> 16 outmasks + threshold records on the host, rc_wait"},
+                        "api": "rc_submit_frames(%d pinned host frames) -> %d outmasks + threshold records on the host, rc_wait" % (FRAMES_PER_STEP, FRAMES_PER_STEP)},
                 "host_binding": "rank pinned to %d GPU-local cores (NVML affinity)" % ncpu_local if ncpu_local else "none",
                 "gpu_launches": int(launches), "clocks": sampler.summary(t_region0, t_region1 + 0.05), "roofline": roofline, "kernels": kernels,
                 "check": {"last_UPPER": float(h_results[(state["step"] - 1) & 1][FRAMES_PER_STEP - 1].UPPER),
