@@ -138,55 +138,102 @@ __device__ __forceinline__ float theta_deg(float y, float x)
     return theta;
 }
 
+// One pixel of vectorToColor: packed b | g << 8 | r << 16; *mag receives |v| (0 for NaN, which never raises the maximum)
+__device__ __forceinline__ unsigned vector_px(float2 f, float prev_max, bool fma, float* mag)
+{
+    const float m = magnitude(f.x, f.y);
+    const unsigned hue = to_uchar(__fdiv_rn(theta_deg(f.y, f.x), 2.f));
+    const unsigned val = to_uchar(__fdiv_rn(__fmul_rn(m, 255.f), prev_max));
+    *mag = m > 0.f ? m : 0.f;
+    return hsv2bgr(hue, 255u, val, fma);
+}
+
+// PX = 4: four adjacent pixels per thread, two 16-byte flow loads and three 32-bit stores (w % 4 == 0, 4-byte aligned
+// image rows); PX = 1: any geometry.
+template <int PX>
 __global__ void __launch_bounds__(256)
 vector_color_kernel(const float* __restrict__ flow, size_t step, int w, int h, uint8_t* __restrict__ bgr, size_t bstep,
                     const float* __restrict__ prev_max, unsigned* __restrict__ new_max, int fma)
 {
-    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
-    float mag = 0.f;
+    const float pm = *prev_max;
+    const int x = (blockIdx.x * 256 + threadIdx.x) * PX, y = blockIdx.y;
+    float best = 0.f;
     if (x < w) {
-        const float2 f = flow_row(flow, step, y)[x];
-        mag = magnitude(f.x, f.y);
-        const unsigned hue = to_uchar(__fdiv_rn(theta_deg(f.y, f.x), 2.f));
-        const unsigned val = to_uchar(__fdiv_rn(__fmul_rn(mag, 255.f), *prev_max));
-        const unsigned p = hsv2bgr(hue, 255u, val, fma != 0);
         uint8_t* o = bgr + (size_t)y * bstep + 3 * (size_t)x;
-        o[0] = (uint8_t)p; o[1] = (uint8_t)(p >> 8); o[2] = (uint8_t)(p >> 16);
-        if (!(mag > 0.f)) mag = 0.f;                                    // NaN / zero never raise the maximum
+        if (PX == 4) {
+            const float4* fp = reinterpret_cast<const float4*>(flow_row(flow, step, y) + x);
+            const float4 a = fp[0], b = fp[1];
+            float m0, m1, m2, m3;
+            const unsigned p0 = vector_px(make_float2(a.x, a.y), pm, fma != 0, &m0), p1 = vector_px(make_float2(a.z, a.w), pm, fma != 0, &m1);
+            const unsigned p2 = vector_px(make_float2(b.x, b.y), pm, fma != 0, &m2), p3 = vector_px(make_float2(b.z, b.w), pm, fma != 0, &m3);
+            unsigned* o4 = reinterpret_cast<unsigned*>(o);
+            o4[0] = p0 | p1 << 24; o4[1] = p1 >> 8 | p2 << 16; o4[2] = p2 >> 16 | p3 << 8;
+            best = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        } else {
+            const unsigned p = vector_px(flow_row(flow, step, y)[x], pm, fma != 0, &best);
+            o[0] = (uint8_t)p; o[1] = (uint8_t)(p >> 8); o[2] = (uint8_t)(p >> 16);
+        }
     }
-    warp_max_nonneg(mag, new_max);
+    warp_max_nonneg(best, new_max);
 }
 
 // ---- shearRateToColor --------------------------------------------------------------------------------------------
+// One pixel: interior pixels get (hue, 255, 255) from the Frobenius norm of the Jacobian, border pixels keep the caller's
+// bytes `old`; both are then converted HSV -> BGR, as the reference's full-image cvtColor does.
+__device__ __forceinline__ unsigned shear_px(const float* __restrict__ flow, size_t step, int w, int h, int x, int y,
+                                             unsigned old, float prev_max, bool fma, float* frob_out)
+{
+    constexpr int OFF = 10;
+    unsigned hh = old & 0xffu, ss = (old >> 8) & 0xffu, vv = (old >> 16) & 0xffu;
+    float frob = 0.f;
+    if (x >= OFF && x < w - OFF && y >= OFF && y < h - OFF) {
+        const float2 above = flow_row(flow, step, y - OFF)[x], below = flow_row(flow, step, y + OFF)[x];
+        const float2 left = flow_row(flow, step, y)[x - OFF], right = flow_row(flow, step, y)[x + OFF];
+        const float j00 = __fsub_rn(right.x, left.x), j01 = __fsub_rn(above.x, below.x);
+        const float j10 = __fsub_rn(right.y, left.y), j11 = __fsub_rn(above.y, below.y);
+        float fr = __fadd_rn(__fmul_rn(j00, j00), __fmul_rn(j01, j01));
+        fr = __fadd_rn(fr, __fmul_rn(j10, j10));
+        fr = __fadd_rn(fr, __fmul_rn(j11, j11));
+        frob = __fsqrt_rn(fr);
+        hh = to_uchar(__fsub_rn(128.f, __fdiv_rn(__fmul_rn(frob, 128.f), prev_max)));
+        ss = 255u; vv = 255u;
+        if (!(frob > 0.f)) frob = 0.f;
+    }
+    *frob_out = frob;
+    return hsv2bgr(hh, ss, vv, fma);
+}
+
+template <int PX>
 __global__ void __launch_bounds__(256)
 shear_color_kernel(const float* __restrict__ flow, size_t step, int w, int h, uint8_t* __restrict__ img, size_t istep,
                    const float* __restrict__ prev_max, unsigned* __restrict__ new_max, int fma)
 {
     constexpr int OFF = 10;
-    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
-    float frob = 0.f;
+    const float pm = *prev_max;
+    const int x = (blockIdx.x * 256 + threadIdx.x) * PX, y = blockIdx.y;
+    float best = 0.f;
     if (x < w) {
         uint8_t* o = img + (size_t)y * istep + 3 * (size_t)x;
-        unsigned hh, ss, vv;
-        if (x >= OFF && x < w - OFF && y >= OFF && y < h - OFF) {
-            const float2 above = flow_row(flow, step, y - OFF)[x], below = flow_row(flow, step, y + OFF)[x];
-            const float2 left = flow_row(flow, step, y)[x - OFF], right = flow_row(flow, step, y)[x + OFF];
-            const float j00 = __fsub_rn(right.x, left.x), j01 = __fsub_rn(above.x, below.x);
-            const float j10 = __fsub_rn(right.y, left.y), j11 = __fsub_rn(above.y, below.y);
-            float fr = __fadd_rn(__fmul_rn(j00, j00), __fmul_rn(j01, j01));
-            fr = __fadd_rn(fr, __fmul_rn(j10, j10));
-            fr = __fadd_rn(fr, __fmul_rn(j11, j11));
-            frob = __fsqrt_rn(fr);
-            hh = to_uchar(__fsub_rn(128.f, __fdiv_rn(__fmul_rn(frob, 128.f), *prev_max)));
-            ss = 255u; vv = 255u;
-            if (!(frob > 0.f)) frob = 0.f;
-        } else {                       // the reference converts the untouched border of the caller's image as well
-            hh = o[0]; ss = o[1]; vv = o[2];
+        if (PX == 4) {
+            unsigned* o4 = reinterpret_cast<unsigned*>(o);
+            unsigned old[4] = {0, 0, 0, 0};
+            if (!(x >= OFF && x + 3 < w - OFF && y >= OFF && y < h - OFF)) {      // some of the four are border pixels
+                const unsigned w0 = o4[0], w1 = o4[1], w2 = o4[2];
+                old[0] = w0 & 0xffffffu; old[1] = (w0 >> 24) | (w1 & 0xffffu) << 8;
+                old[2] = (w1 >> 16) | (w2 & 0xffu) << 16; old[3] = w2 >> 8;
+            }
+            unsigned p[4]; float m[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) p[i] = shear_px(flow, step, w, h, x + i, y, old[i], pm, fma != 0, &m[i]);
+            o4[0] = p[0] | p[1] << 24; o4[1] = p[1] >> 8 | p[2] << 16; o4[2] = p[2] >> 16 | p[3] << 8;
+            best = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+        } else {
+            const unsigned old = (unsigned)o[0] | (unsigned)o[1] << 8 | (unsigned)o[2] << 16;
+            const unsigned p = shear_px(flow, step, w, h, x, y, old, pm, fma != 0, &best);
+            o[0] = (uint8_t)p; o[1] = (uint8_t)(p >> 8); o[2] = (uint8_t)(p >> 16);
         }
-        const unsigned p = hsv2bgr(hh, ss, vv, fma != 0);
-        o[0] = (uint8_t)p; o[1] = (uint8_t)(p >> 8); o[2] = (uint8_t)(p >> 16);
     }
-    warp_max_nonneg(frob, new_max);
+    warp_max_nonneg(best, new_max);
 }
 
 }  // namespace
@@ -214,7 +261,10 @@ void rc_launch_vector_color(rc_ctx* c, const float* flow, size_t step, int w, in
 {
     cudaMemsetAsync(d_new_max, 0, 4, c->stream);
     KScope ks(c, K_DIAG, 11.0 * w * h);
-    vector_color_kernel<<<dim3((w + 255) / 256, h), 256, 0, c->stream>>>(flow, step, w, h, bgr, bstep, d_prev_max, d_new_max, fma);
+    const bool v4 = w % 4 == 0 && bstep % 4 == 0 && step % 16 == 0 && (reinterpret_cast<uintptr_t>(bgr) & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(flow) & 15) == 0;
+    if (v4) vector_color_kernel<4><<<dim3((w / 4 + 255) / 256, h), 256, 0, c->stream>>>(flow, step, w, h, bgr, bstep, d_prev_max, d_new_max, fma);
+    else vector_color_kernel<1><<<dim3((w + 255) / 256, h), 256, 0, c->stream>>>(flow, step, w, h, bgr, bstep, d_prev_max, d_new_max, fma);
 }
 
 void rc_launch_shear_color(rc_ctx* c, const float* flow, size_t step, int w, int h, uint8_t* img, size_t istep,
@@ -222,5 +272,7 @@ void rc_launch_shear_color(rc_ctx* c, const float* flow, size_t step, int w, int
 {
     cudaMemsetAsync(d_new_max, 0, 4, c->stream);
     KScope ks(c, K_DIAG, 11.0 * w * h);
-    shear_color_kernel<<<dim3((w + 255) / 256, h), 256, 0, c->stream>>>(flow, step, w, h, img, istep, d_prev_max, d_new_max, fma);
+    const bool v4 = w % 4 == 0 && istep % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0;
+    if (v4) shear_color_kernel<4><<<dim3((w / 4 + 255) / 256, h), 256, 0, c->stream>>>(flow, step, w, h, img, istep, d_prev_max, d_new_max, fma);
+    else shear_color_kernel<1><<<dim3((w + 255) / 256, h), 256, 0, c->stream>>>(flow, step, w, h, img, istep, d_prev_max, d_new_max, fma);
 }
