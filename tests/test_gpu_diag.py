@@ -107,3 +107,25 @@ def test_hsv2bgr_golden_through_shear_border(ctx):
         img = rows[:n].reshape(16, n // 16, 3).copy()                           # 16 rows <= 2*offset: no interior
         ctx.shear_rate_to_color(np.zeros((16, n // 16, 2), np.float32), img, 1.0)
         assert np.array_equal(img.reshape(-1, 3), z[k + "_bgr"].reshape(-1, 3)[:n]), k
+
+
+def test_error_paths(ctx):
+    """Bad arguments come back as negative codes (no crash, no CPU fallback): NULL pointers, bad geometry, missing state."""
+    import ctypes as C
+    from ripcurrents_b200 import Context
+    lib = ctx.lib
+    fl = np.zeros((8, 8, 2), np.float32); img = np.zeros((8, 8, 3), np.uint8)
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    none = C.c_void_p(0)
+    assert lib.rc_vector_to_color(ctx.h, p(fl), C.c_size_t(64), C.c_int(8), C.c_int(8), none, C.c_size_t(24), None, C.c_int(0)) == -1
+    assert lib.rc_vector_to_color(ctx.h, p(fl), C.c_size_t(8), C.c_int(8), C.c_int(8), p(img), C.c_size_t(24), None, C.c_int(0)) == -1
+    assert lib.rc_shear_rate_to_color(ctx.h, p(fl), C.c_size_t(64), C.c_int(8), C.c_int(8), p(img), C.c_size_t(8), None, C.c_int(0)) == -1
+    assert lib.rc_subtract_mean_magnitude(ctx.h, none, C.c_size_t(64), C.c_int(8), C.c_int(8), C.c_int(0), None) == -1
+    assert lib.rc_particle_fields(ctx.h, none, none, C.c_int(8), C.c_int(8), C.c_int(0), none, none, none, none, none, None) == -1
+    assert lib.rc_particle_fields(ctx.h, p(fl), none, C.c_int(8), C.c_int(8), C.c_int(0), none, none, p(img), none, none, None) == -1
+    assert lib.rc_normalize_jet(ctx.h, none, C.c_size_t(4), none, none, None) == -1
+    assert lib.rc_streamline_positions(ctx.h, p(fl), C.c_int(0), C.c_int(8), p(fl), C.c_int(0)) == -1
+    fresh = Context(0)                                   # flow == NULL means "the context's last flow": none yet
+    assert lib.rc_vector_to_color(fresh.h, none, C.c_size_t(0), C.c_int(0), C.c_int(0), p(img), C.c_size_t(24), None, C.c_int(0)) == -4
+    fresh.close()
+    assert lib.rc_vector_to_color(None, p(fl), C.c_size_t(64), C.c_int(8), C.c_int(8), p(img), C.c_size_t(24), None, C.c_int(0)) == -1
