@@ -1356,8 +1356,59 @@ flow_strip_kernel(FlowArgs a, int SEG)
             }
             return fi;
         };
+        // emits row yo of the final flow (+ its histogram contribution)
+        auto emit = [&](int yo, float2 f) {
+            if (col_out) outp[yo * w + xv] = f;
+            if (do_hist) {
+                const int key = col_out ? hist_key_fast(f.x, f.y) : -1;
+                const unsigned peers = __match_any_sync(0xffffffffu, key);
+                if (key >= 0 && (int)(__ffs(peers) - 1) == lane) {
+                    if (atomicAdd(&sH[key], __popc(peers)) == 0) {
+                        const int slot = atomicAdd(&sNKeys, 1);
+                        if (slot < 256) sKeys[slot] = (unsigned short)key;
+                    }
+                }
+            }
+        };
+        // blur of level `it` at row r - 1 from the two stored rows and the new one, then the 2x2 solve
+        auto blur_solve = [&](int it, int r, const float (&C)[5]) {
+            float sv[5];
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                const float ra = sWin[wrp][it][r & 1][c][lane];          // row r-2
+                const float rb = sWin[wrp][it][(r - 1) & 1][c][lane];    // row r-1
+                const float vs = BOX ? rb + (ra + C[c]) : fmaf(ra + C[c], k1, rb * k0);
+                const float lft = __shfl_up_sync(0xffffffffu, vs, 1), rgt = __shfl_down_sync(0xffffffffu, vs, 1);
+                sv[c] = (BOX ? vs + (lft + rgt) : fmaf(lft + rgt, k1, vs * k0)) * ps;
+            }
+            return solve_fast(sv[0], sv[1], sv[2], sv[3], sv[4]);
+        };
+        // Rows [vs0, vs1] are the steady state: every level has its two previous rows, every row index is inside the
+        // image and every iteration emits one output row, so the loop body needs none of the warm-up / bottom-edge tests.
+        const int vs0 = vbeg + 2 * NT + 2, vs1 = min(vend, h - 1);
 #pragma unroll 1
         for (int v = vbeg; v <= vend; v++) {
+            if (v >= vs0 && v <= vs1) {
+                float2 f;
+#pragma unroll
+                for (int it = 0; it < NT; it++) {
+                    const int r = v - it;
+                    float C[5];
+                    if (it == 0) {
+                        const float2 fi = init_flow(r);
+                        update_matrices_core<false>(x, r, fi.x, fi.y, w, h, R0, R1, pitch, C);
+                    } else {
+                        if (need_fix) { f.x = __shfl_sync(0xffffffffu, f.x, src_lane); f.y = __shfl_sync(0xffffffffu, f.y, src_lane); }
+                        update_matrices_core<false>(x, r, f.x, f.y, w, h, R0, R1, pitch, C);
+                    }
+                    f = blur_solve(it, r, C);
+#pragma unroll
+                    for (int c = 0; c < 5; c++) sWin[wrp][it][r & 1][c][lane] = C[c];
+                    nfed[it]++;
+                }
+                emit(v - NT, f);
+                continue;
+            }
             bool produced = false;
             float2 f = make_float2(0.f, 0.f);
 #pragma unroll
@@ -1389,16 +1440,7 @@ flow_strip_kernel(FlowArgs a, int SEG)
                     continue;
                 }
                 if (nfed[it] >= 2) {
-                    float sv[5];
-#pragma unroll
-                    for (int c = 0; c < 5; c++) {
-                        const float ra = sWin[wrp][it][r & 1][c][lane];          // row r-2
-                        const float rb = sWin[wrp][it][(r - 1) & 1][c][lane];    // row r-1
-                        const float vs = BOX ? rb + (ra + C[c]) : fmaf(ra + C[c], k1, rb * k0);
-                        const float lft = __shfl_up_sync(0xffffffffu, vs, 1), rgt = __shfl_down_sync(0xffffffffu, vs, 1);
-                        sv[c] = (BOX ? vs + (lft + rgt) : fmaf(lft + rgt, k1, vs * k0)) * ps;
-                    }
-                    f = solve_fast(sv[0], sv[1], sv[2], sv[3], sv[4]);
+                    f = blur_solve(it, r, C);
                     produced = true;
                 }
 #pragma unroll
@@ -1406,20 +1448,7 @@ flow_strip_kernel(FlowArgs a, int SEG)
                 nfed[it]++;
             }
             const int yo = v - NT;
-            const bool row_out = produced && yo >= y0 && yo < y0 + SEG && yo < h;      // warp-uniform
-            if (row_out) {
-                if (col_out) outp[yo * w + xv] = f;
-                if (do_hist) {
-                    const int key = col_out ? hist_key_fast(f.x, f.y) : -1;
-                    const unsigned peers = __match_any_sync(0xffffffffu, key);
-                    if (key >= 0 && (int)(__ffs(peers) - 1) == lane) {
-                        if (atomicAdd(&sH[key], __popc(peers)) == 0) {
-                            const int slot = atomicAdd(&sNKeys, 1);
-                            if (slot < 256) sKeys[slot] = (unsigned short)key;
-                        }
-                    }
-                }
-            }
+            if (produced && yo >= y0 && yo < y0 + SEG && yo < h) emit(yo, f);      // warp-uniform
         }
     }
     if (do_hist) {
