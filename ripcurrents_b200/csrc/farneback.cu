@@ -1317,14 +1317,11 @@ flow_strip_kernel(FlowArgs a, int SEG)
 {
     constexpr int UW = 32 - 2 * NT;
     __shared__ unsigned int sH[RC_HIST_CELLS];
-    __shared__ unsigned short sKeys[256];
-    __shared__ int sNKeys;
     __shared__ float sWin[8][NT][2][5][32];
     const int w = a.w, h = a.h, j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, pitch = a.pitch;
     const bool do_hist = a.hist_delta != nullptr;
     if (do_hist) {
         for (int i = tid; i < RC_HIST_CELLS; i += 256) sH[i] = 0;
-        if (tid == 0) sNKeys = 0;
         __syncthreads();
     }
     const int sx0 = (blockIdx.y * 8 + wrp) * UW;             // grid = (pairs, strip groups, segments), pair fastest
@@ -1362,12 +1359,7 @@ flow_strip_kernel(FlowArgs a, int SEG)
             if (do_hist) {
                 const int key = col_out ? hist_key_fast(f.x, f.y) : -1;
                 const unsigned peers = __match_any_sync(0xffffffffu, key);
-                if (key >= 0 && (int)(__ffs(peers) - 1) == lane) {
-                    if (atomicAdd(&sH[key], __popc(peers)) == 0) {
-                        const int slot = atomicAdd(&sNKeys, 1);
-                        if (slot < 256) sKeys[slot] = (unsigned short)key;
-                    }
-                }
+                if (key >= 0 && (int)(__ffs(peers) - 1) == lane) atomicAdd(&sH[key], __popc(peers));
             }
         };
         // blur of level `it` at row r - 1 from the two stored rows and the new one, then the 2x2 solve
@@ -1454,13 +1446,8 @@ flow_strip_kernel(FlowArgs a, int SEG)
     if (do_hist) {
         __syncthreads();
         unsigned int* dst = a.hist_delta + (size_t)j * RC_HIST_CELLS;
-        const int nk = sNKeys;
-        if (nk <= 256) {
-            if (tid < nk) { const int k = sKeys[tid]; atomicAdd(&dst[k], sH[k]); }
-        } else {
-            for (int i = tid; i < RC_HIST_CELLS; i += 256)
-                if (sH[i]) atomicAdd(&dst[i], sH[i]);
-        }
+        for (int i = tid; i < RC_HIST_CELLS; i += 256)
+            if (sH[i]) atomicAdd(&dst[i], sH[i]);
     }
 }
 
