@@ -387,7 +387,7 @@ def run_ours(args, rank, world, local_rank):
                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                     "alg_bytes_per_launch": v["bytes"] / v["launches"], "avg_launch_us": 1e3 * v["ms"] / v["launches"],
                     "share_of_step": round(v["ms"] / total_ms, 4),
-                    "note": "the fused layer kernel is bound by instruction issue (ncu: ~70 % of issue slots, ~770 "
+                    "note": "the fused layer kernel is bound by instruction issue (ncu: ~70 % of issue slots, ~700 "
                             "thread-instructions per pixel, DRAM 13 %), not by HBM: see DESIGN.md section 7"}
         tfile = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu capture
         try:
