@@ -807,6 +807,16 @@ __device__ __forceinline__ float2 solve_fast(float g11, float g12, float g22, fl
     return make_float2(det2(g11, h2, g12, h1) * idet, det2(g22, h1, g12, h2) * idet);
 }
 
+// The same solve on UNSCALED window sums S = s / ps (box windows): numerators and determinant both carry 1/ps^2, so only
+// the regulariser changes: eps = 1e-3 / ps^2.  Saves the five post-scale multiplies; the reciprocal is the hardware
+// approximation (1 ulp) -- both far below the 1e-3 px tolerance of the fast path (strict mode has its own solve).
+__device__ __forceinline__ float2 solve_fast_unscaled(float g11, float g12, float g22, float h1, float h2, float eps)
+{
+    float idet;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(idet) : "f"(det2(g11, g22, g12, g12) + eps));
+    return make_float2(det2(g11, h2, g12, h1) * idet, det2(g22, h1, g12, h2) * idet);
+}
+
 // one updateFlow iteration, per-pixel reference form: blur(M[mi]) -> solve -> (fused updateMatrices -> M[mi^1] | flow)
 template <bool FUSE>
 __global__ void update_flow_strict_kernel(FlowArgs a, int mi)
@@ -1336,7 +1346,8 @@ flow_strip_kernel(FlowArgs a, int SEG)
         const float2* coarse = a.coarse ? reinterpret_cast<const float2*>(a.coarse + (size_t)j * a.coarse_stride) : nullptr;
         int csx = 0; float cfx = 0.f;
         if (coarse) resize_coef(x, a.cw, a.sxs, csx, cfx);
-        const float k0 = a.win.k[0], k1 = a.win.k[1], ps = a.win.post_scale;
+        const float k0 = a.win.k[0], k1 = a.win.k[1];
+        const float eps_unscaled = 1e-3f / (a.win.post_scale * a.win.post_scale);     // post_scale is 1 for Gaussian windows
         float2* outp = reinterpret_cast<float2*>(a.out(j));
 
         int nfed[NT];
@@ -1371,9 +1382,9 @@ flow_strip_kernel(FlowArgs a, int SEG)
                 const float rb = sWin[wrp][it][(r - 1) & 1][c][lane];    // row r-1
                 const float vs = BOX ? rb + (ra + C[c]) : fmaf(ra + C[c], k1, rb * k0);
                 const float lft = __shfl_up_sync(0xffffffffu, vs, 1), rgt = __shfl_down_sync(0xffffffffu, vs, 1);
-                sv[c] = (BOX ? vs + (lft + rgt) : fmaf(lft + rgt, k1, vs * k0)) * ps;
+                sv[c] = BOX ? vs + (lft + rgt) : fmaf(lft + rgt, k1, vs * k0);
             }
-            return solve_fast(sv[0], sv[1], sv[2], sv[3], sv[4]);
+            return solve_fast_unscaled(sv[0], sv[1], sv[2], sv[3], sv[4], eps_unscaled);
         };
         // Rows [vs0, vs1] are the steady state: every level has its two previous rows, every row index is inside the
         // image and every iteration emits one output row, so the loop body needs none of the warm-up / bottom-edge tests.
@@ -1468,7 +1479,11 @@ __device__ __forceinline__ int hist_key_fast(float x, float y)
     if (y < 0) a = __fsub_rn(360.f, a);
     float mag = __fsqrt_rn(fmaf(x, x, __fmul_rn(y, y)));
     int bin = (int)__fmul_rn(mag, (float)RC_HIST_RESOLUTION);
-    int dir = (int)__fdiv_rn(__fmul_rn(a, (float)RC_HIST_DIRECTIONS), 360.f);
+    // (int)(a * 36 / 360) with the division as multiply + two FMAs (Markstein): the truncated result was checked against
+    // IEEE division for every float in [0, 12960] (it differs only for denormal quotients, which truncate to 0 either way)
+    const float t = __fmul_rn(a, (float)RC_HIST_DIRECTIONS), rc360 = 1.0f / 360.0f;
+    const float q0 = __fmul_rn(t, rc360);
+    int dir = (int)__fmaf_rn(__fmaf_rn(-q0, 360.f, t), rc360, q0);
     if (bin < RC_HIST_BINS && bin >= 0) return dir * RC_HIST_BINS + bin;
     return -1;
 }
