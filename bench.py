@@ -37,10 +37,11 @@ if ROOT not in sys.path:
 W, H = 1920, 1080
 PARAMS = (0.5, 2, 3, 2, 15, 1.2, 0)      # ripcurrents.cpp:215
 WINDOW = 10                               # main.cpp:1084
-# frames per step = the context's max_batch: one batched launch sequence per step.  Measured on one B200 (pairs/s,
-# device-resident): 8 -> 7.9 k, 16 -> 8.45 k, 32 -> 8.8 k, 64 -> 9.1 k (fewer partial waves per launch); 32 keeps the
-# buffering of a live stream at about one second.  RC_BENCH_BATCH overrides it (<= 64).
-FRAMES_PER_STEP = int(os.environ.get("RC_BENCH_BATCH", "32"))
+# frames per step = the context's max_batch (64 = RC_MAX_BATCH): one batched launch sequence per step.  Measured on one
+# B200 (pairs/s, device-resident): 8 -> 8.0 k, 16 -> 8.9 k, 32 -> 9.4 k, 64 -> 9.7 k (fewer partial waves per launch); the
+# reference reads recorded video, so the two seconds of buffering at 30 fps cost nothing there -- a live stream would
+# configure a smaller max_batch.  RC_BENCH_BATCH overrides it (<= 64).
+FRAMES_PER_STEP = int(os.environ.get("RC_BENCH_BATCH", "64"))
 CLIP_FRAMES = FRAMES_PER_STEP + 1         # distinct synthetic frames per rank, played 0..B,B-1..1 (ping-pong, period 2B =
                                           # two steps) so that consecutive frames always differ by one motion step
 METRIC = "1080p Farneback flow+aggregation frame pairs/s"
