@@ -388,8 +388,18 @@ def run_ours(args, rank, world, local_rank):
                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                     "alg_bytes_per_launch": v["bytes"] / v["launches"], "avg_launch_us": 1e3 * v["ms"] / v["launches"],
                     "share_of_step": round(v["ms"] / total_ms, 4),
-                    "note": "the fused layer kernel is bound by instruction issue (ncu: ~70 % of issue slots, ~700 "
-                            "thread-instructions per pixel, DRAM 13 %), not by HBM: see DESIGN.md section 7"}
+                    "note": "algorithmic bytes are those of the kernel AS BUILT (the fused layer: 50 B per pixel and layer); "
+                            "SURVEY 8(d) budgets 170 B per pixel and layer for the same work done as one updateMatrices + T "
+                            "updateFlow passes (see survey_bytes).  The fused kernel is bound by instruction issue (ncu: "
+                            "~70 % of issue slots, ~700 thread-instructions per pixel, DRAM 13 %), not by HBM: DESIGN.md "
+                            "section 7"}
+        if dom == "flow_layer_fused":
+            # the same launches measured against SURVEY.md 8(d)'s per-pixel figure for this step of the path
+            # (62 + 80 (T - 1) + 28 bytes per pixel and layer at T iterations, T = 2 here)
+            sv = v["bytes"] / 50.0 * (62.0 + 80.0 * (PARAMS[3] - 1) + 28.0)
+            roofline["survey_bytes"] = {"per_launch": sv / v["launches"],
+                                        "achieved": round(sv / (v["ms"] * 1e-3) / 1e9, 1),
+                                        "frac": round(sv / (v["ms"] * 1e-3) / 1e9 / peak, 4)}
         tfile = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu capture
         try:
             roofline["traffic"] = json.load(open(tfile)).get(dom)
