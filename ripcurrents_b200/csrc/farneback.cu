@@ -1003,7 +1003,10 @@ flow_layer_kernel(FlowArgs a)
     }
     __syncthreads();
 
-    const float k0 = a.win.k[0], k1 = a.win.k[1], ps = a.win.post_scale;
+    // same arithmetic as flow_strip_kernel (unscaled sums, regulariser eps / ps^2): the two forms give identical bits, so
+    // results do not depend on which one a launch size selects
+    const float k0 = a.win.k[0], k1 = a.win.k[1];
+    const float eps_unscaled = 1e-3f / (a.win.post_scale * a.win.post_scale);
 #pragma unroll
     for (int it = 0; it < NT; it++) {
         constexpr int dummy = 0; (void)dummy;
@@ -1044,15 +1047,15 @@ flow_layer_kernel(FlowArgs a)
                         const float v0 = win[1][0][c] + (win[0][0][c] + win[2][0][c]);
                         const float v1 = win[1][1][c] + (win[0][1][c] + win[2][1][c]);
                         const float v2 = win[1][2][c] + (win[0][2][c] + win[2][2][c]);
-                        s[c] = (v1 + (v0 + v2)) * ps;
+                        s[c] = v1 + (v0 + v2);
                     } else {
                         const float v0 = fmaf(win[0][0][c] + win[2][0][c], k1, win[1][0][c] * k0);
                         const float v1 = fmaf(win[0][1][c] + win[2][1][c], k1, win[1][1][c] * k0);
                         const float v2 = fmaf(win[0][2][c] + win[2][2][c], k1, win[1][2][c] * k0);
-                        s[c] = fmaf(v0 + v2, k1, v1 * k0) * ps;
+                        s[c] = fmaf(v0 + v2, k1, v1 * k0);
                     }
                 }
-                f = solve_fast(s[0], s[1], s[2], s[3], s[4]);
+                f = solve_fast_unscaled(s[0], s[1], s[2], s[3], s[4], eps_unscaled);
             }
             if (last) {
                 const int x = x0 + col, y = y0 + r;

@@ -19,16 +19,19 @@ def test_fused_layer_variant(kernel):
     assert out.returncode == 0 and "variant ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
-@pytest.mark.parametrize("var,val", [("RC_PYR", "separate")])
+@pytest.mark.parametrize("var,val", [("RC_PYR", "separate"), ("RC_FLOW_KERNEL", "strip")])
 def test_alternative_kernels_give_identical_bits(tmp_path, var, val):
-    """pyr3_kernel (layers 0-2 in one pass over the frame) against the per-layer pyramid kernels: same arithmetic, so
-    the flows must agree bit for bit."""
+    """pyr3_kernel (layers 0-2 in one pass over the frame) against the per-layer pyramid kernels, and the strip form of
+    the fused flow layer (forced on every launch) against the tile form these small launches select by default: same
+    arithmetic, so the flows must agree bit for bit -- results do not depend on the batch size that picks the kernel."""
     import numpy as np
     outs = []
     for mode in ("default", "alt"):
         env = dict(os.environ)
         if mode == "alt":
             env[var] = val
+            if var == "RC_FLOW_KERNEL":
+                env["RC_STRIP_MINPX"] = "0"
         path = str(tmp_path / (mode + ".npz"))
         out = subprocess.run([sys.executable, os.path.join(HERE, "pyr_dump.py"), path], env=env, capture_output=True, text=True,
                              timeout=600)
