@@ -122,15 +122,20 @@ ingest_bgr_kernel(const uint8_t* __restrict__ bgr, size_t step, size_t fstride, 
 
 // Mask clean-up: create_edges, ripcurrents_module.cpp:216-220 -- dilate with OpenCV's
 // 5x5 ellipse, then morphological gradient (dilate - erode) with the same element; taps outside the image are ignored.
-// One 32x32 tile per CTA, both stages in shared memory (halo 4), any number of masks per launch (blockIdx.z).
-__device__ __forceinline__ bool ell5(int dx, int dy) { return dy == -2 || dy == 2 ? dx == 0 : true; }
+// One 32x32 tile per CTA, all stages in shared memory (halo 4), any number of masks per launch (blockIdx.z).
+// The ellipse is a 5-wide x 3-tall rectangle plus the centre column of rows +-2, so each max / min is a 5-wide row pass
+// followed by three rows of it and two centre taps: 8 compares per pixel and stage instead of 21.
+__device__ __forceinline__ int max5(const uint8_t* p) { return max(max(max((int)p[0], (int)p[1]), max((int)p[2], (int)p[3])), (int)p[4]); }
+__device__ __forceinline__ int min5(const uint8_t* p) { return min(min(min((int)p[0], (int)p[1]), min((int)p[2], (int)p[3])), (int)p[4]); }
 
 __global__ void __launch_bounds__(256)
 edges_kernel(const uint8_t* __restrict__ mask, size_t step, size_t stride, int w, int h, uint8_t* __restrict__ out,
              size_t ostep, size_t ostride)
 {
-    __shared__ uint8_t sIn[40][40];
-    __shared__ uint8_t sD[36][36];
+    __shared__ uint8_t sIn[40][40];                    // mask on (y0-4.., x0-4..), 0 outside the image
+    __shared__ uint8_t sH[38][36];                     // 5-wide row maximum of sIn: rows y0-3.., columns x0-2..
+    __shared__ uint8_t sDx[36][36], sDn[36][36];       // dilated mask on (y0-2.., x0-2..); outside the image 0 / 255
+    __shared__ uint8_t sHx[34][32], sHn[34][32];       // 5-wide row maximum of sDx / minimum of sDn: rows y0-1.., columns x0..
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32, tid = threadIdx.x;
     mask += (size_t)blockIdx.z * stride;
     out += (size_t)blockIdx.z * ostride;
@@ -139,34 +144,33 @@ edges_kernel(const uint8_t* __restrict__ mask, size_t step, size_t stride, int w
         sIn[cy][cx] = (x >= 0 && y >= 0 && x < w && y < h) ? mask[(size_t)y * step + x] : 0;
     }
     __syncthreads();
+    for (int i = tid; i < 38 * 36; i += 256) {
+        const int r = i / 36, c = i - r * 36;
+        sH[r][c] = (uint8_t)max5(&sIn[r + 1][c]);
+    }
+    __syncthreads();
     for (int i = tid; i < 36 * 36; i += 256) {
         const int cy = i / 36, cx = i - cy * 36, x = x0 - 2 + cx, y = y0 - 2 + cy;
-        int v = 0;
-        if (x >= 0 && y >= 0 && x < w && y < h) {
-#pragma unroll
-            for (int dy = -2; dy <= 2; dy++)
-#pragma unroll
-                for (int dx = -2; dx <= 2; dx++)
-                    if (ell5(dx, dy)) v = max(v, (int)sIn[cy + 2 + dy][cx + 2 + dx]);
-        }
-        sD[cy][cx] = (uint8_t)v;
+        const bool inside = x >= 0 && y >= 0 && x < w && y < h;
+        const int v = max(max(max((int)sH[cy][cx], (int)sH[cy + 1][cx]), max((int)sH[cy + 2][cx], (int)sIn[cy][cx + 2])),
+                          (int)sIn[cy + 4][cx + 2]);
+        sDx[cy][cx] = inside ? (uint8_t)v : 0;
+        sDn[cy][cx] = inside ? (uint8_t)v : 255;
+    }
+    __syncthreads();
+    for (int i = tid; i < 34 * 32; i += 256) {
+        const int r = i >> 5, c = i & 31;
+        sHx[r][c] = (uint8_t)max5(&sDx[r + 1][c]);
+        sHn[r][c] = (uint8_t)min5(&sDn[r + 1][c]);
     }
     __syncthreads();
     for (int i = tid; i < 32 * 32; i += 256) {
         const int cy = i >> 5, cx = i & 31, x = x0 + cx, y = y0 + cy;
         if (x >= w || y >= h) continue;
-        int dd = 0, de = 255;
-#pragma unroll
-        for (int dy = -2; dy <= 2; dy++)
-#pragma unroll
-            for (int dx = -2; dx <= 2; dx++)
-                if (ell5(dx, dy)) {
-                    const int xx = x + dx, yy = y + dy;
-                    if (xx >= 0 && yy >= 0 && xx < w && yy < h) {
-                        const int p = sD[cy + 2 + dy][cx + 2 + dx];
-                        dd = max(dd, p); de = min(de, p);
-                    }
-                }
+        const int dd = max(max(max((int)sHx[cy][cx], (int)sHx[cy + 1][cx]), max((int)sHx[cy + 2][cx], (int)sDx[cy][cx + 2])),
+                           (int)sDx[cy + 4][cx + 2]);
+        const int de = min(min(min((int)sHn[cy][cx], (int)sHn[cy + 1][cx]), min((int)sHn[cy + 2][cx], (int)sDn[cy][cx + 2])),
+                           (int)sDn[cy + 4][cx + 2]);
         out[(size_t)y * ostep + x] = (uint8_t)(dd - de);
     }
 }
