@@ -54,3 +54,15 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".h", ".hpp", ".cpp", ".cuh")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "rc_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_header_is_plain_c_and_cpp(tmp_path):
+    """include/ripcurrents_b200.h must compile as C99 and as C++11 on its own (no torch / CUDA / OpenCV types in the ABI)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "ripcurrents_b200.h")
+    src_c = tmp_path / "t.c"; src_c.write_text('#include "ripcurrents_b200.h"\nint main(void) { return rc_version() < 0; }\n')
+    src_cpp = tmp_path / "t.cpp"; src_cpp.write_text('#include "ripcurrents_b200.h"\nint main() { rc_ctx* c = nullptr; return c != nullptr; }\n')
+    inc = os.path.dirname(hdr)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src_c)])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src_cpp)])
