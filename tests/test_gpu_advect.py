@@ -94,3 +94,20 @@ def test_advect_on_context_flow(ctx, oracle):
     oracle.advect(flow, ref, 1.0, 1, 0.0, oracle.ADV_PATHLINE)
     ctx.advect(None, seeds, 1.0, 1, 0.0, 0)
     assert np.array_equal(seeds.view(np.uint32), ref.view(np.uint32))
+
+
+def test_empty_and_degenerate_inputs(ctx, oracle):
+    """No seeds, no emitters, zero iterations, a streakline that is already full: calls succeed and leave data alone."""
+    flow = (np.random.default_rng(0).standard_normal((32, 48, 2)) * 2).astype(np.float32)
+    ctx.advect(flow, np.empty((0, 2), np.float32), 1.0, 1, 0.0, 0)                       # nothing to move
+    seeds = np.array([[5.5, 6.5], [40.0, 20.0]], np.float32); keep = seeds.copy()
+    ctx.advect(flow, seeds, 1.0, 0, 0.0, 0)                                               # zero iterations
+    assert np.array_equal(seeds, keep)
+    ctx.streakline_step(flow, np.empty((0, 2), np.float32), np.empty((0, 4, 2), np.float32), np.empty(0, np.int32))
+    em = np.array([[10.0, 10.0]], np.float32)
+    verts = np.zeros((1, 3, 2), np.float32); verts[0, :, :] = [[10, 10], [11, 11], [12, 12]]
+    cnt = np.array([3], np.int32)                                                         # capacity reached
+    rv, rc = verts.copy(), cnt.copy()
+    oracle.streakline_step(flow, em, rv, rc)
+    ctx.streakline_step(flow, em, verts, cnt)
+    assert np.array_equal(cnt, rc) and np.array_equal(verts[0, :cnt[0]], rv[0, :rc[0]])
