@@ -148,10 +148,15 @@ def run_reference(args, rank, world):
             if time.perf_counter() - t_all > 200 and len(vals) >= 1:
                 break
     value = float(np.mean(vals))
+    # a step of this arm is a bounded SAMPLE of the workload (per * workers pairs), not the GPU arm's 64-frame batch:
+    # ms_per_step and config.frames_per_step both describe that sample
+    cfg = config_dict(args.gpus)
+    cfg["frames_per_step"] = per * workers
+    cfg["sample_of"] = "%d-frame steps of the GPU arm" % FRAMES_PER_STEP
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * per * workers / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (+f64 accumulators)",
-            "data": "synthetic moving texture", "config": config_dict(args.gpus),
+            "data": "synthetic moving texture", "config": cfg,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

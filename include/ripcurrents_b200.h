@@ -177,6 +177,15 @@ int rc_window_configure(rc_ctx* ctx, int w, int h, int W);
 int rc_window_update(rc_ctx* ctx, const float* flow, size_t flow_step);
 int rc_window_get(rc_ctx* ctx, float* avg, size_t avg_step);
 int rc_window_device(rc_ctx* ctx, float** dev_avg);
+/* averageVector's window update (ripcurrents_module.cpp:392-400, declared at ripcurrents.hpp:48), one pass per frame:
+ *   average -= old_slot / frames;  new = the get_delta field of `flow` (every pixel: one step of dt from displacement 0
+ *   at its own position, cut-off r > upper; module:396-398 calls get_delta(&pixel, x, y, current, 2, UPPER));
+ *   average += new / frames.
+ * old_slot: the buffer entry being replaced (w*h*2 fp32; NULL = zeros); average: w*h*2 fp32 in/out; new_slot (may be NULL)
+ * receives the new field.  All dense; host or device pointers (all of one kind).  The reference passes its buffer vector BY
+ * VALUE, so its caller's slot is never rewritten -- the header-compatible wrapper reproduces that. */
+int rc_average_vector(rc_ctx* ctx, const float* old_slot, const float* flow, size_t flow_step, int w, int h, float* average,
+                      float* new_slot, int frames, float dt, float upper);
 /* subtructAverage (ripcurrents_module.cpp:810-863): flow -= mean(flow); in place; mean_xy[2] out (may be NULL) */
 int rc_subtract_mean(rc_ctx* ctx, float* flow, size_t flow_step, int w, int h, double* mean_xy);
 

@@ -29,8 +29,8 @@ def _nvcc():
 
 
 def _deps(src):
-    return [src, os.path.join(CSRC, "rc_internal.h"), os.path.join(HERE, "..", "include", "ripcurrents_b200.h"),
-            os.path.abspath(__file__)]
+    return [src, os.path.join(CSRC, "rc_internal.h"), os.path.join(CSRC, "atan2f_ref.h"),
+            os.path.join(HERE, "..", "include", "ripcurrents_b200.h"), os.path.abspath(__file__)]
 
 
 def build(force=False, verbose=False):
@@ -54,7 +54,10 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % s)
     if rebuilt or not os.path.exists(SO):
-        cmd = [_nvcc(), "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        # --cudart shared: the library carries only the runtime symbols it uses (libcudart.so.12 resolves through the
+        # rpath below, or is already loaded by torch in the bench / tests)
+        cmd = [_nvcc(), "-shared", "--cudart", "shared", "-o", SO] + objs + [
+            "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         subprocess.check_call(cmd)
     return SO
 

@@ -23,7 +23,7 @@ SYMBOLS = [
     "rc_hist_reset", "rc_polar_hist", "rc_hist_get", "rc_hist_add", "rc_hist_device", "rc_cart_to_polar",
     "rc_thresholds", "rc_accumulator_reset", "rc_classify_accumulate", "rc_accumulator_get",
     "rc_accumulator_device", "rc_window_configure", "rc_window_update", "rc_window_get", "rc_window_device",
-    "rc_subtract_mean", "rc_batch_hist", "rc_aggregate_last", "rc_accumulator_mask", "rc_mask_edges", "rc_ingest_bgr", "rc_submit_frames_bgr", "rc_hist_from_polar", "rc_create_flow", "rc_create_accumulationbuffer", "rc_advect", "rc_streakline_step", "rc_process_frame",
+    "rc_subtract_mean", "rc_average_vector", "rc_batch_hist", "rc_aggregate_last", "rc_accumulator_mask", "rc_mask_edges", "rc_ingest_bgr", "rc_submit_frames_bgr", "rc_hist_from_polar", "rc_create_flow", "rc_create_accumulationbuffer", "rc_advect", "rc_streakline_step", "rc_process_frame",
     "rc_particle_fields", "rc_normalize_jet", "rc_ratio_jet", "rc_field_magnitude", "rc_streamline_positions",
     "rc_subtract_mean_magnitude", "rc_vector_to_color", "rc_shear_rate_to_color",
 ]
@@ -276,6 +276,18 @@ class Context:
         avg = np.empty((h, w, 2), np.float32)
         self._chk(self.lib.rc_window_get(self.h, _ptr(avg), C.c_size_t(w * 8)))
         return avg
+
+    def average_vector(self, old_slot, flow, average, frames=300, dt=2.0, upper=0.0, want_new=False):
+        """averageVector's window update (module:392-400); `average` (h,w,2) f32 numpy is updated in place."""
+        flow = np.ascontiguousarray(flow, np.float32)
+        h, w, _ = flow.shape
+        assert average.dtype == np.float32 and average.flags.c_contiguous and average.shape == (h, w, 2)
+        if old_slot is not None:
+            old_slot = np.ascontiguousarray(old_slot, np.float32)
+        new = np.empty((h, w, 2), np.float32) if want_new else None
+        self._chk(self.lib.rc_average_vector(self.h, _ptr(old_slot), _ptr(flow), C.c_size_t(w * 8), C.c_int(w), C.c_int(h),
+                                             _ptr(average), _ptr(new), C.c_int(frames), C.c_float(dt), C.c_float(upper)))
+        return new
 
     def subtract_mean(self, flow):
         assert isinstance(flow, np.ndarray) and flow.dtype == np.float32 and flow.flags.c_contiguous

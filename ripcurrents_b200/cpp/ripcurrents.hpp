@@ -73,6 +73,12 @@ void get_streamlines(cv::Mat& streamout, cv::Mat& streamoverlay_color, cv::Mat& 
 void create_histogram(cv::Mat current, int hist[HIST_BINS], int& histsum, int hist2d[HIST_DIRECTIONS][HIST_BINS],
                       int histsum2d[HIST_DIRECTIONS], float& UPPER, float UPPER2d[HIST_DIRECTIONS],
                       float prop_above_upper[HIST_DIRECTIONS]);
+// ripcurrents.hpp:48 / ripcurrents_module.cpp:386-400: the sliding-window update of the 300-frame flow average.  Exactly as
+// in the reference `buffer` is a BY-VALUE vector, so the caller's slot is not rewritten; average_color, grid and
+// max_displacement belong to the arrow / colour visualisation that follows in the reference (module:402-484) and are
+// not touched.
+void averageVector(std::vector<cv::Mat> buffer, cv::Mat& current, int update_ith_buffer, cv::Mat& average,
+                   cv::Mat& average_color, double** grid, float max_displacement, float UPPER);
 void create_flow(cv::Mat current, cv::Mat waterclass, cv::Mat accumulator2, float UPPER, float MID, float LOWER,
                  float UPPER2d[HIST_DIRECTIONS]);
 void create_accumulationbuffer(cv::Mat& accumulator, cv::Mat accumulator2, cv::Mat& out, cv::Mat outmask, int framecount);

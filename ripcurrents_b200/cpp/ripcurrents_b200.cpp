@@ -124,6 +124,7 @@ void window_average(std::vector<cv::Mat>& buffer, int& currentBuffer, const cv::
 }  // namespace rc
 
 // ---- ripcurrents.hpp -------------------------------------------------------------------------------------------------
+static cv::Mat dense_mat(const cv::Mat& m) { return m.isContinuous() ? m : m.clone(); }
 static void one_seed(Pixel2* pt, const cv::Mat& flow, float dt, int iterations, float upper, int variant, float* dist,
                      int xo, int yo)
 {
@@ -210,6 +211,18 @@ void create_histogram(cv::Mat current, int hist[HIST_BINS], int& histsum, int hi
         while (b > targetbin) { threshsum3 += hist2d[angle][b]; b--; }
         prop_above_upper[angle] = ((float)threshsum3) / threshsum;
     }
+}
+
+void averageVector(std::vector<cv::Mat> buffer, cv::Mat& current, int update_ith_buffer, cv::Mat& average, cv::Mat&, double**,
+                   float, float UPPER)
+{
+    require(update_ith_buffer >= 0 && update_ith_buffer < (int)buffer.size(), "averageVector: buffer index");
+    cv::Mat old = dense_mat(buffer[update_ith_buffer]);
+    require(current.type() == CV_32FC2 && average.type() == CV_32FC2 && old.type() == CV_32FC2 && average.isContinuous() &&
+            average.rows == current.rows && average.cols == current.cols && old.rows == current.rows && old.cols == current.cols,
+            "averageVector: CV_32FC2 current / average / buffer of one size required");
+    check(rc_average_vector(rc::default_context(), old.ptr<float>(), current.ptr<float>(), current.step, current.cols,
+                            current.rows, average.ptr<float>(), nullptr, BUFFER_FRAME, 2.f, UPPER), "rc_average_vector");
 }
 
 void create_flow(cv::Mat current, cv::Mat waterclass, cv::Mat accumulator2, float UPPER, float MID, float LOWER,

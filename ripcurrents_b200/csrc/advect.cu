@@ -107,6 +107,28 @@ streakline_kernel(FlowView F, const float* __restrict__ emitters, int E, const f
     if (grow && blockIdx.x == 0 && threadIdx.x == 0) out[0] = reinterpret_cast<const float2*>(emitters)[e];
 }
 
+// averageVector's window update (ripcurrents_module.cpp:392-400) in one pass: per pixel
+//   average -= old / frames;  new = get_delta(pixel = 0, home (x, y), flow, dt, UPPER);  average += new / frames
+// (`Mat / s` scales by (float)(1.0 / s), oracle/aggregate_oracle.c); new_slot (optional) receives the new field.
+__global__ void __launch_bounds__(256)
+average_vector_kernel(FlowView F, const float* __restrict__ old_slot, float* __restrict__ average,
+                      float* __restrict__ new_slot, float inv, float dt, float upper)
+{
+    const size_t n = (size_t)F.w * F.h;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % (size_t)F.w), y = (int)(i / (size_t)F.w);
+    float2 p = make_float2(0.f, 0.f);
+    float dx, dy;
+    if (gather(F, (float)x, (float)y, dx, dy) && !(__fsqrt_rn(dx * dx + dy * dy) > upper)) { p.x = p.x + dx * dt; p.y = p.y + dy * dt; }
+    float2 a = reinterpret_cast<float2*>(average)[i];
+    const float2 o = old_slot ? reinterpret_cast<const float2*>(old_slot)[i] : make_float2(0.f, 0.f);
+    a.x = (a.x - o.x * inv) + p.x * inv;
+    a.y = (a.y - o.y * inv) + p.y * inv;
+    reinterpret_cast<float2*>(average)[i] = a;
+    if (new_slot) reinterpret_cast<float2*>(new_slot)[i] = p;
+}
+
 __global__ void streakline_count_kernel(int32_t* count, int E, int cap)
 {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,6 +145,16 @@ void rc_launch_advect(rc_ctx* c, const float* flow, size_t flow_step, int w, int
     KScope ks(c, K_ADVECT, (16.0 + (dist ? 8.0 : 0.0)) * n + 8.0 * w * h);
     advect_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(F, seeds, n, dt, iterations, upper, variant, dist,
                                                                      home);
+}
+
+void rc_launch_average_vector(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, const float* old_slot,
+                              float* average, float* new_slot, int frames, float dt, float upper)
+{
+    FlowView F{reinterpret_cast<const char*>(flow), flow_step, w, h};
+    const size_t n = (size_t)w * h;
+    KScope ks(c, K_WINDOW, (8.0 + (old_slot ? 8.0 : 0.0) + 16.0 + (new_slot ? 8.0 : 0.0)) * n);
+    average_vector_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(F, old_slot, average, new_slot,
+                                                                             (float)(1.0 / (double)frames), dt, upper);
 }
 
 // vertices is updated out of place into `vout` by the caller-provided scratch; the launcher copies back.

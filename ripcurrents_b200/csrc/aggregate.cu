@@ -176,12 +176,14 @@ classify_kernel(const float* __restrict__ flow, size_t flow_step, int w, int h, 
 // 1 B mask written.  (ripcurrents.cpp:376-439 + main.cpp:1143-1153, in the reference's order.)
 __global__ void __launch_bounds__(256)
 classify_batch_kernel(ClassifyBatch cb, size_t n4, size_t n, const float* __restrict__ thr_batch, int framecount0,
-                      float* __restrict__ acc, uint8_t* __restrict__ masks, float* __restrict__ avg, float inv_w)
+                      float* __restrict__ acc, uint8_t* __restrict__ masks, float* __restrict__ avg, float inv_w, int vec)
 {
     const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= n4) return;
     const size_t i = i4 * 4;
-    const bool full = i + 3 < n;
+    // vec: the host checked that w*h % 4 == 0 and that every flow / ring / mask / accumulator pointer is 16-byte (masks:
+    // 4-byte) aligned -- odd image sizes put every other ring slot and mask row off alignment and take the scalar path
+    const bool full = vec && i + 3 < n;
     float av[4]; float2 mean[4];
     if (full) {
         float4 t = *reinterpret_cast<const float4*>(acc + i);
@@ -360,9 +362,12 @@ void rc_launch_classify_batch(rc_ctx* c, const ClassifyBatch& cb, int w, int h, 
     const float inv = W > 0 ? (float)(1.0 / (double)W) : 0.f;
     int nold = 0;
     for (int j = 0; j < cb.nb; j++) nold += (avg && cb.old[j]) ? 1 : 0;
+    auto al = [](const void* p, size_t a) { return (reinterpret_cast<size_t>(p) & (a - 1)) == 0; };
+    bool vec = n % 4 == 0 && al(acc, 16) && al(avg, 16) && al(masks, 4);
+    for (int j = 0; j < cb.nb && vec; j++) vec = al(cb.flow[j], 16) && al(cb.old[j], 16);
     KScope ks(c, K_CLASSIFY, ((8.0 + (masks ? 1.0 : 0.0)) * cb.nb + 8.0 * nold + 8.0 + (avg ? 16.0 : 0.0)) * n);
     classify_batch_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, c->stream>>>(cb, n4, n, thr_batch, framecount0, acc, masks,
-                                                                              avg, inv);
+                                                                              avg, inv, vec ? 1 : 0);
 }
 
 void rc_launch_widen_counts(rc_ctx* c, const unsigned int* in, long long* out, size_t n)

@@ -35,6 +35,10 @@ int fail(rc_ctx* c, int code, const char* fmt, const char* detail = "")
 #define CHECK_LAUNCH(c)                                                                       \
     do {                                                                                      \
         cudaError_t _e = cudaGetLastError();                                                  \
+        if (!(c)->launch_err.empty()) {                                                       \
+            const std::string _m = (c)->launch_err; (c)->launch_err.clear();                  \
+            return fail((c), RC_ERR_CUDA, "kernel launch failed: %s", _m.c_str());            \
+        }                                                                                     \
         if (_e != cudaSuccess) return fail((c), RC_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(_e)); \
     } while (0)
 
@@ -87,7 +91,7 @@ void free_farneback(rc_ctx* c)
         c->pending_results[s] = nullptr; c->pending_count[s] = 0;
     }
     c->flow_ring = nullptr; c->ring_slots = 0; c->d_avg = nullptr; c->d_hist_delta = nullptr;
-    c->configured = false; c->nlayers = 0; c->frames_seen = 0; c->n_flows = 0; c->pairs_done = 0; c->submitted = 0;
+    c->configured = false; c->nlayers = 0; c->frames_seen = 0; c->n_flows = 0; c->pairs_done = 0; c->win_start = 0; c->submitted = 0;
 }
 
 int round_half_even(double v) { return (int)nearbyint(v); }
@@ -199,7 +203,7 @@ int ensure_flow_ring(rc_ctx* c)
     CUDA_TRY(c, cudaMemsetAsync(c->flow_ring, 0, per * want, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->d_avg, 0, per, c->stream));
     c->ring_slots = want;
-    c->pairs_done = 0;
+    c->pairs_done = 0; c->win_start = 0;
     return RC_OK;
 }
 
@@ -269,7 +273,7 @@ int run_frames(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, 
             for (int j = 0; j < nb; j++) {
                 cb.flow[j] = dst[j];
                 const long long p = c->pairs_done + j;
-                cb.old[j] = (c->win_W > 0 && p >= c->win_W) ? ring_slot(c, p - c->win_W) : nullptr;
+                cb.old[j] = (c->win_W > 0 && p - c->win_start >= c->win_W) ? ring_slot(c, p - c->win_W) : nullptr;
             }
             // framecount of a flow = the caller's loop counter of the frame that completed the pair
             rc_launch_classify_batch(c, cb, w, h, thr, framecount0 + done, c->d_acc,
@@ -398,6 +402,7 @@ int rc_create(rc_ctx** out, int device)
     rc_ctx* c = new (std::nothrow) rc_ctx();
     if (!c) return RC_ERR_NOMEM;
     c->device = device;
+    rc_farneback_init_device(device);
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -506,8 +511,12 @@ int rc_flow_configure_batch(rc_ctx* c, int w, int h, double pyr_scale, int level
     p.w = w; p.h = h; p.pyr_scale = pyr_scale; p.levels = levels; p.winsize = winsize; p.iterations = iterations;
     p.poly_n = poly_n; p.poly_sigma = poly_sigma; p.flags = flags; p.max_batch = max_batch;
     if (c->configured && c->prm == p) {
+        // restart of the stream (a new clip): the next frame primes, and the sliding window starts from zero buffers
+        // like the reference's (main.cpp:1084-1092) -- flows of the previous clip never leave a mean they did not enter
         sync_all(c);
         c->frames_seen = 0; c->n_flows = 0;
+        c->win_start = c->pairs_done;
+        if (c->d_avg) CUDA_TRY(c, cudaMemsetAsync(c->d_avg, 0, sizeof(float) * 2 * (size_t)w * h, c->stream));
         return RC_OK;
     }
     free_farneback(c);
@@ -833,6 +842,7 @@ int rc_window_configure(rc_ctx* c, int w, int h, int W)
     if (c->configured) {
         int rc = ensure_flow_ring(c); if (rc) return rc;
         CUDA_TRY(c, cudaMemsetAsync(c->d_avg, 0, sizeof(float) * 2 * (size_t)c->prm.w * c->prm.h, c->stream));
+        c->win_start = c->pairs_done;      // re-armed: the ring's older flows were never added to the new mean
     }
     if (W == 0) return RC_OK;
     // stand-alone window for caller-provided flows (rc_window_update)
@@ -898,6 +908,40 @@ int rc_window_device(rc_ctx* c, float** dev_avg)
     float* src = active_avg(c, &w, &h);
     if (!src) return fail(c, RC_ERR_STATE, "rc_window_configure has not been called%s");
     *dev_avg = src;
+    return RC_OK;
+}
+
+int rc_average_vector(rc_ctx* c, const float* old_slot, const float* flow, size_t flow_step, int w, int h, float* average,
+                      float* new_slot, int frames, float dt, float upper)
+{
+    if (!c || !flow || !average || w < 1 || h < 1 || frames < 1 || flow_step < (size_t)w * 8) return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    const size_t nb = (size_t)w * h * 8;
+    const bool dev = is_device_ptr(average);
+    if ((old_slot && is_device_ptr(old_slot) != dev) || (new_slot && is_device_ptr(new_slot) != dev) || is_device_ptr(flow) != dev)
+        return fail(c, RC_ERR_INVALID, "old_slot / flow / average / new_slot must all be host or all be device pointers%s");
+    const float *d_old = old_slot, *d_flow = flow; float *d_avg = average, *d_new = new_slot; size_t d_step = flow_step;
+    if (!dev) {
+        int rc = ensure(c, &c->d_tmp2, &c->d_tmp2_cap, 4 * nb); if (rc) return rc;
+        char* base = reinterpret_cast<char*>(c->d_tmp2);
+        float* df = reinterpret_cast<float*>(base); d_avg = reinterpret_cast<float*>(base + nb);
+        CUDA_TRY(c, cudaMemcpy2DAsync(df, (size_t)w * 8, flow, flow_step, (size_t)w * 8, h, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(d_avg, average, nb, cudaMemcpyHostToDevice, c->stream));
+        d_flow = df; d_step = (size_t)w * 8;
+        if (old_slot) {
+            float* dold = reinterpret_cast<float*>(base + 2 * nb);
+            CUDA_TRY(c, cudaMemcpyAsync(dold, old_slot, nb, cudaMemcpyHostToDevice, c->stream));
+            d_old = dold;
+        }
+        if (new_slot) d_new = reinterpret_cast<float*>(base + 3 * nb);
+    }
+    rc_launch_average_vector(c, d_flow, d_step, w, h, d_old, d_avg, d_new, frames, dt, upper);
+    CHECK_LAUNCH(c);
+    if (!dev) {
+        CUDA_TRY(c, cudaMemcpyAsync(average, d_avg, nb, cudaMemcpyDeviceToHost, c->stream));
+        if (new_slot) CUDA_TRY(c, cudaMemcpyAsync(new_slot, d_new, nb, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
     return RC_OK;
 }
 

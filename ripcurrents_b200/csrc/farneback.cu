@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include "rc_internal.h"
 #include <cuda_pipeline.h>
+#include <mutex>
 
 namespace {
 
@@ -1519,6 +1520,31 @@ hist_batch_kernel(FlowArgs a, int n)
 // ===================================================================================================
 // launchers
 // ===================================================================================================
+// Opt-in dynamic shared memory sizes: set ONCE per device (cudaFuncSetAttribute is per device), from rc_create, under a
+// std::once_flag -- contexts on several GPUs may be created and driven from different threads.
+void rc_farneback_init_device(int device)
+{
+    static std::once_flag once[64];
+    std::call_once(once[device & 63], [] {
+        const int strict_max = (int)(sizeof(float) * ((size_t)(32 + 2 * RC_MAX_POLY_N) * (64 + 2 * RC_MAX_POLY_N) +
+                                                      3 * (size_t)32 * (64 + 2 * RC_MAX_POLY_N)));
+        cudaFuncSetAttribute(polyexp_strict_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, strict_max);
+        cudaFuncSetAttribute(pyr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        const int tiled_max = (int)(sizeof(float) * ((size_t)(16 + 32) * (64 + 32) + 16 * (size_t)(64 + 32)));
+        cudaFuncSetAttribute(flow_iter_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled_max);
+        cudaFuncSetAttribute(flow_iter_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled_max);
+        const int big = (int)(sizeof(float) * (16 * 5 * 84 + 36 * 5 * 64));
+#define RC_CFG1(MM, FU, BX) \
+    cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
+    cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)
+#define RC_CFG(MM) RC_CFG1(MM, true, true); RC_CFG1(MM, true, false); RC_CFG1(MM, false, true); RC_CFG1(MM, false, false)
+        RC_CFG(2); RC_CFG(5); RC_CFG(10);
+#undef RC_CFG
+#undef RC_CFG1
+        cudaGetLastError();
+    });
+}
+
 static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
 {
     const int nslots = c->B + 1;
@@ -1543,11 +1569,6 @@ static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
     constexpr int TX = 64, TY = 32;
     const int n = c->poly.n;
     const size_t smem = sizeof(float) * ((size_t)(TY + 2 * n) * (TX + 2 * n) + 3 * (size_t)TY * (TX + 2 * n));
-    static size_t configured[64] = {0};      // cudaFuncSetAttribute is per device
-    if (smem > configured[c->device & 63]) {
-        cudaFuncSetAttribute(polyexp_strict_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured[c->device & 63] = smem;
-    }
     dim3 g((L.w + TX - 1) / TX, (L.h + TY - 1) / TY, nb);
     polyexp_strict_kernel<TX, TY><<<g, 256, smem, c->stream>>>(L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot,
                                                               nslots, c->poly);
@@ -1630,11 +1651,6 @@ void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fs
             smem = sizeof(float2) * (size_t)(a.SRH | 1) * a.TXD + 4 * (size_t)a.SRH * a.SRW + 8 * (size_t)(a.TXD + a.TYD) +
                    4 * (size_t)a.SRW;
             if (smem <= 100 * 1024) break;
-        }
-        static size_t configured[64] = {0};  // per device
-        if (smem > configured[c->device & 63] && smem > 48 * 1024) {
-            cudaFuncSetAttribute(pyr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured[c->device & 63] = smem;
         }
         {
             dim3 g((L.w + a.TXD - 1) / a.TXD, (L.h + a.TYD - 1) / a.TYD, nb);
@@ -1735,14 +1751,6 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
             else update_matrices_kernel<false><<<g, b, 0, c->stream>>>(a, 0);
         }
         const size_t tsm = sizeof(float) * ((size_t)(16 + 2 * m) * (64 + 2 * m) + 16 * (size_t)(64 + 2 * m));
-        if (tiled && tsm > 48 * 1024) {
-            static size_t configured[64] = {0};   // per device
-            if (tsm > configured[c->device & 63]) {
-                cudaFuncSetAttribute(flow_iter_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-                cudaFuncSetAttribute(flow_iter_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-                configured[c->device & 63] = tsm;
-            }
-        }
         dim3 gt(nb, (L.w + 63) / 64, (L.h + 15) / 16);
         const bool box = !c->win.gaussian;
         const bool spec = march;      // marching kernel; other half-widths use the generic square-tile kernel
@@ -1751,20 +1759,6 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         const int MSEG = march_seg_env > 0 ? march_seg_env : ((L.h + mnseg - 1) / mnseg + 3) & ~3;
         dim3 gm(nb, (L.w + 63) / 64, (L.h + MSEG - 1) / MSEG);
         const size_t msm = sizeof(float) * (16 * 5 * (size_t)((64 + 2 * m + 3) & ~3) + (size_t)(16 + 2 * m) * 5 * 64);
-        if (spec) {
-            static bool configured[64] = {false};
-            if (!configured[c->device & 63]) {
-                const int big = (int)(sizeof(float) * (16 * 5 * 84 + 36 * 5 * 64));
-#define RC_CFG1(MM, FU, BX) \
-    cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
-    cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)
-#define RC_CFG(MM) RC_CFG1(MM, true, true); RC_CFG1(MM, true, false); RC_CFG1(MM, false, true); RC_CFG1(MM, false, false)
-                RC_CFG(2); RC_CFG(5); RC_CFG(10);
-#undef RC_CFG
-#undef RC_CFG1
-                configured[c->device & 63] = true;
-            }
-        }
         bool hist_fused = false;
         int mi = 0;
         for (int it = 0; it < T; it++) {

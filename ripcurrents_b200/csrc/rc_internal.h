@@ -79,6 +79,7 @@ struct rc_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
+    std::string launch_err;        // first failed kernel launch since the last CHECK_LAUNCH (kernel class + CUDA error)
     int64_t launches = 0;
 
     bool prof_on = false;
@@ -107,6 +108,7 @@ struct rc_ctx {
     int ring_slots = 0;
     long long pairs_done = 0;      // total flows produced since configure
     int win_W = 0;                 // sliding-window length (0 = off)
+    long long win_start = 0;       // pair index at which the window was (re)armed: flows before it never entered the mean
     float* d_avg = nullptr;        // window mean (w*h*2)
 
     // staging for host frames (double-buffered) and outputs
@@ -165,11 +167,17 @@ struct KScope {
     }
     ~KScope()
     {
+        // launch status: a bad configuration (grid, shared memory, registers) surfaces here, named by kernel class,
+        // instead of at some later runtime call
+        const cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess && c->launch_err.empty())
+            c->launch_err = std::string(rc_kernel_names[id]) + ": " + cudaGetErrorString(e);
         if (a) { cudaEventRecord(b, c->stream); c->prof.push_back(ProfRec{id, a, b, bytes}); }
     }
 };
 
 // ---- farneback.cu ----------------------------------------------------------------------------------
+void rc_farneback_init_device(int device);     // once per device: opt-in shared-memory sizes of the kernels
 // Expands `nb` new frames (device, dense u8, frame stride `fstride`) into R ring slots first_slot.. (mod B+1).
 void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, int nb, int first_slot);
 // Flows for `nb` consecutive pairs: pair j = (ring slot (prev_slot + j) % (B+1), next slot); layer-0 flow of pair j
@@ -230,5 +238,7 @@ void rc_launch_shear_color(rc_ctx* c, const float* flow, size_t step, int w, int
 // ---- advect.cu -------------------------------------------------------------------------------------
 void rc_launch_advect(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float* seeds, size_t n, float dt,
                       int iterations, float upper, int variant, float* dist, const int32_t* home);
+void rc_launch_average_vector(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, const float* old_slot,
+                              float* average, float* new_slot, int frames, float dt, float upper);
 void rc_launch_streakline(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, const float* emitters, int E,
                           float* vertices, int32_t* count, int cap, float dt);

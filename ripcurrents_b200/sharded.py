@@ -31,13 +31,20 @@ def exclusive_prefix_counts(all_counts, rank):
     return out
 
 
-def run_block(backend, frames, lo, hi, framecount_of_pair, dist=None, device=None):
+def run_block(backend, frames, lo, hi, framecount_of_pair, dist=None, device=None, base_counts=None):
     """Processes pairs [lo, hi) of `frames` (frame i and i+1 form pair i) on this rank and combines across ranks.
 
+    Every pair that precedes ANY rank's [lo, hi) of this call must already be inside `base_counts` (int64 [37, 50], the
+    global cumulative counts of earlier calls; None = nothing earlier): a long stream is processed in super-blocks of
+    world * B pairs, rank r taking the r-th run of B (run_stream below).
+
     backend.flows_and_counts(frames[lo:hi+1])        -> int64 [hi-lo, 37, 50] per-frame counts (flows stay inside)
-    backend.aggregate(prefix_counts, framecounts)    -> list of per-frame UPPER thresholds; adds into backend's accumulator
-    backend.accumulator() / set_accumulator(a)       -> float32 [h*w] (numpy)
-    Returns dict(upper=[...this rank's frames], counts_total=int64[37,50], accumulator=float32[h*w] (global)).
+    backend.aggregate(prefix_counts, framecounts)    -> per-frame UPPER thresholds; prefix_counts = the cumulative counts of
+                                                        every frame before this rank's first one (the backend SETS its
+                                                        counters to it); adds into the backend's own accumulator
+    backend.accumulator()                            -> float32 [h*w] (numpy): this rank's contributions so far
+    Returns dict(upper=[...this rank's frames], counts_total=int64[37,50] (all ranks, THIS call),
+                 accumulator=float32[h*w] (all ranks, all calls so far)).
     """
     import torch
     world = dist.get_world_size() if dist is not None else 1
@@ -58,22 +65,41 @@ def run_block(backend, frames, lo, hi, framecount_of_pair, dist=None, device=Non
     else:
         all_counts = [counts]
     prefix = exclusive_prefix_counts(all_counts, rank)
+    if base_counts is not None:
+        prefix = prefix + np.asarray(base_counts, np.int64)
     uppers = backend.aggregate(prefix, [framecount_of_pair(p) for p in range(lo, hi)]) if n_local > 0 else []
     acc = backend.accumulator()
     if world > 1:
         t = torch.from_numpy(acc.copy())
         if device is not None:
             t = t.to(device)
-        dist.all_reduce(t)
+        dist.all_reduce(t)          # integer-valued sums: exact in any order; the backend keeps its own contributions
         acc = t.cpu().numpy()
-        backend.set_accumulator(acc)
     total = sum((c.sum(0) for c in all_counts if c.shape[0]), np.zeros((37, 50), np.int64))
     return {"upper": uppers, "counts_total": total, "accumulator": acc}
 
 
+def run_stream(backend, frames, B, framecount_of_pair, dist=None, device=None):
+    """A whole clip in super-blocks of world * B pairs (rank r takes the r-th run of B pairs of each super-block), carrying
+    the global cumulative counts from one super-block to the next.  Returns dict(upper={pair: UPPER} for this rank's
+    pairs, counts_total, accumulator (global, after the last super-block))."""
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    n_pairs = len(frames) - 1
+    base = np.zeros((37, 50), np.int64)
+    uppers, res = {}, None
+    for s0 in range(0, n_pairs, world * B):
+        lo = min(s0 + rank * B, n_pairs)
+        hi = min(lo + B, n_pairs)
+        res = run_block(backend, frames, lo, hi, framecount_of_pair, dist, device, base)
+        uppers.update({lo + i: u for i, u in enumerate(res["upper"])})
+        base = base + res["counts_total"]
+    return {"upper": uppers, "counts_total": base, "accumulator": res["accumulator"] if res else backend.accumulator()}
+
+
 class GpuBackend:
-    """The C-ABI engine: rc_flow_push_batch -> rc_batch_hist -> rc_hist_add(prefix) -> rc_aggregate_last.
-    One block of at most max_batch pairs per run_block call."""
+    """The C-ABI engine: rc_flow_push_batch -> rc_batch_hist -> counters := prefix -> rc_aggregate_last.
+    At most max_batch pairs per call; re-entrant (run_block / run_stream may call it once per super-block)."""
 
     def __init__(self, ctx, w, h, params, max_batch):
         self.ctx, self.w, self.h, self.P, self.B = ctx, w, h, tuple(params), max_batch
@@ -86,7 +112,8 @@ class GpuBackend:
         frames = np.ascontiguousarray(frames, np.uint8)
         n_pairs = frames.shape[0] - 1
         if n_pairs > self.B:
-            raise ValueError("block larger than max_batch: call run_block once per sub-block")
+            raise ValueError("block of %d pairs is larger than max_batch = %d: use run_stream, which walks a clip in "
+                             "super-blocks of world * max_batch pairs" % (n_pairs, self.B))
         self.ctx.flow_configure_batch(self.w, self.h, *self.P, self.B)   # restart: the block's first frame primes
         assert self.ctx.flow_push_batch(frames[:1]) == 0
         assert self.ctx.flow_push_batch(frames[1:]) == n_pairs
@@ -94,6 +121,9 @@ class GpuBackend:
         return self.ctx.batch_hist(n_pairs)
 
     def aggregate(self, prefix_counts, framecounts):
+        # the device counters become exactly "every frame before this rank's first one" (earlier super-blocks of all ranks
+        # + lower ranks of this one); whatever an earlier call left there is discarded
+        self.ctx.hist_reset()
         self.ctx.hist_add(prefix_counts)
         res = self.ctx.aggregate_last(self._nb, framecounts[0])
         return [float(r.UPPER) for r in res]
@@ -101,6 +131,3 @@ class GpuBackend:
     def accumulator(self):
         p, w, h = self.ctx.accumulator_device()
         return self.ctx.accumulator_get(w, h).ravel()
-
-    def set_accumulator(self, acc):
-        self.global_accumulator = acc     # reporting copy; the device keeps this rank's own contribution

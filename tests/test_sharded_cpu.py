@@ -38,11 +38,8 @@ class OracleBackend:
     def accumulator(self):
         return self.acc
 
-    def set_accumulator(self, a):
-        self.acc = a
 
-
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, chunked=False):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from oracle import oracle as O
@@ -52,9 +49,13 @@ def _worker(rank, world, port, q):
     w, h, n = 96, 64, 8
     fr = np.stack(synth.clip(w, h, n, seed=3))
     P = (0.5, 1, 3, 2, 5, 1.1, 0)
-    lo, hi = sharded.block_range(n - 1, world, rank)
-    res = sharded.run_block(OracleBackend(O, P, w, h), fr, lo, hi, lambda p: 28 + p, dist=dist)
-    q.put((rank, lo, hi, res["upper"], res["counts_total"], res["accumulator"]))
+    if chunked:      # super-blocks of world * 2 pairs: 7 pairs = two full super-blocks (one ragged) -> three calls
+        res = sharded.run_stream(OracleBackend(O, P, w, h), fr, 2, lambda p: 28 + p, dist=dist)
+        q.put((rank, sorted(res["upper"].items()), res["counts_total"], res["accumulator"]))
+    else:
+        lo, hi = sharded.block_range(n - 1, world, rank)
+        res = sharded.run_block(OracleBackend(O, P, w, h), fr, lo, hi, lambda p: 28 + p, dist=dist)
+        q.put((rank, lo, hi, res["upper"], res["counts_total"], res["accumulator"]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -96,3 +97,33 @@ def test_two_rank_sharding_matches_sequential(oracle):
         assert np.array_equal(g[4], st.hist2d)
         assert np.array_equal(g[5], acc)
     assert acc.sum() > 0
+
+
+def test_two_rank_stream_in_super_blocks_matches_sequential(oracle):
+    """Several run_block calls on the same backends (the cumulative counts must carry across calls): a 7-pair
+    clip in super-blocks of 2 ranks x 2 pairs equals the sequential order frame by frame."""
+    from ripcurrents_b200 import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(2)])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    w, h, n = 96, 64, 8
+    fr = np.stack(synth.clip(w, h, n, seed=3))
+    P = (0.5, 1, 3, 2, 5, 1.1, 0)
+    st = oracle.HistState(); acc = np.zeros(w * h, np.float32); ups = {}
+    for i in range(n - 1):
+        f = oracle.farneback(fr[i], fr[i + 1], *P)
+        oracle.histogram(f, st)
+        ups[i], _, _ = oracle.thresholds(st)
+        oracle.classify_accumulate(f, ups[i], 28 + i, acc)
+    assert [p for p, _ in got[0][1]] == [0, 1, 4, 5] and [p for p, _ in got[1][1]] == [2, 3, 6]
+    assert dict(got[0][1] + got[1][1]) == ups
+    for g in got:
+        assert np.array_equal(g[2], st.hist2d)
+        assert np.array_equal(g[3], acc)
