@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs per worker for the CPU legs (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations (C2-Gaussian, C3, C4)")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle check of the benched configuration")
     return ap.parse_args()
 
 
@@ -214,6 +216,181 @@ class ClockSampler:
         pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
                 "samples": len(rows), "power_w_max": max(pw) if pw else None}
+
+
+# ------------------------------------------------------------------------------------------------ secondary configurations
+def survey_bytes_per_pair(w, h, P, layers, aggregation=True):
+    """n0 + sum_k (118 + 80 (T - 1)) n_k for the flow, + (25 + 40) n0 for aggregation + window mean."""
+    T = P[3]
+    n0 = w * h
+    nk = sum(lw * lh for lw, lh in layers)
+    return n0 + (118 + 80 * (T - 1)) * nk + (65 * n0 if aggregation else 0)
+
+
+def pyramid_layers(w, h, pyr_scale, levels):
+    out, scale = [], 1.0
+    k = 0
+    while k < levels:
+        scale *= pyr_scale
+        if w * scale < 32 or h * scale < 32:
+            break
+        k += 1
+    scale = 1.0
+    for _ in range(k + 1):
+        out.append((int(np.rint(w * scale)), int(np.rint(h * scale))))
+        scale *= pyr_scale
+    return out
+
+
+def measure_flow_config(torch, dev, stream, name, ref, w, h, P, B, steps, peak, sampler):
+    """One secondary line: flow + aggregation + window mean of a device-resident clip through rc_process_frames."""
+    from ripcurrents_b200 import Context, synth
+    frames = synth.clip(w, h, B + 1, seed=5)
+    order = list(range(B + 1)) + list(range(B - 1, 0, -1))
+    d_seq = torch.from_numpy(np.stack([frames[i] for i in order])).to(dev)
+    ctx = Context(dev.index)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.flow_configure_batch(w, h, *P, B)
+    ctx.hist_reset()
+    ctx.window_configure(w, h, WINDOW)
+    NBY = w * h * B
+    st = {"s": 0}
+
+    def step():
+        s = st["s"]
+        ctx.process_frames(d_seq.data_ptr() + (s & 1) * NBY, 31 + s * B, None, want_results=False, count=B)
+        st["s"] = s + 1
+
+    step(); step(); step()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    ctx.profile_reset(); ctx.profile_enable(True)
+    step(); step()
+    torch.cuda.synchronize(dev)
+    prof = ctx.profile_read(); ctx.profile_enable(False)
+    ctx.close()
+    del d_seq
+    torch.cuda.empty_cache()
+    pairs = B * steps
+    value = pairs / (ms * 1e-3)
+    by = survey_bytes_per_pair(w, h, P, pyramid_layers(w, h, P[0], P[1]))
+    tot = sum(v["ms"] for v in prof.values()) or 1.0
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    dgb = dom[1]["bytes"] / (dom[1]["ms"] * 1e-3) / 1e9
+    return {"name": name, "reference_call_site": ref, "workload": "%dx%d Farneback%s + aggregation + window mean W=%d" % (w, h, str(P), WINDOW),
+            "value": value, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "frames_per_step": B,
+            "roofline": {"bound": "hbm", "scope": "whole step on SURVEY 8(d) algorithmic bytes", "bytes_per_pair": by,
+                         "achieved": round(by * value / 1e9, 1), "peak": peak, "unit": "GB/s", "frac": round(by * value / 1e9 / peak, 4),
+                         "pairs_per_s_at_100pct": round(peak * 1e9 / by, 1)},
+            "dominant_kernel": {"name": dom[0], "share": round(dom[1]["ms"] / tot, 4), "avg_us": round(1e3 * dom[1]["ms"] / dom[1]["launches"], 1),
+                                "alg_GBps": round(dgb, 1), "frac": round(dgb / peak, 4)},
+            "kernel_shares": {k: round(v["ms"] / tot, 4) for k, v in prof.items()},
+            "clocks": sampler.summary(t0, t1 + 0.05)}
+
+
+def measure_advection(torch, dev, stream, steps, peak, sampler):
+    """BASELINE configs[3]: per 1080p frame one pathline step of 1 M seeds, the per-pixel particle field and one streakline
+    frame of 3 495 emitters x 299 vertices, on a device-resident flow."""
+    from ripcurrents_b200 import Context, synth
+    fr = np.stack(synth.clip(W, H, 3, seed=0))
+    c = Context(dev.index)
+    c.set_stream(stream.cuda_stream)
+    c.flow_configure_batch(W, H, *PARAMS, 2)
+    c.flow_push_batch(fr[:1]); c.flow_push_batch(fr[1:])
+    rng = np.random.default_rng(1)
+    n = 1 << 20
+    seeds = torch.from_numpy((rng.random((n, 2)) * [W - 3, H - 3] + 1).astype(np.float32)).to(dev)
+    field = torch.zeros((H * W, 2), device=dev); dist = torch.zeros(H * W, device=dev)
+    E, cap = 3495, 300
+    em = torch.from_numpy((rng.random((E, 2)) * [W - 3, H - 3] + 1).astype(np.float32)).to(dev)
+    verts = torch.zeros((E, cap, 2), device=dev); verts[:, 0] = em
+    cnt = torch.full((E,), cap - 1, dtype=torch.int32, device=dev)
+
+    def step():
+        c.advect(None, seeds.data_ptr(), 1.0, 1, 0.0, 0, n=n)
+        c.advect(None, field.data_ptr(), 2.0, 1, 2.0, 5, dist=dist.data_ptr(), n=W * H)
+        c.streakline_step(None, em.data_ptr(), verts.data_ptr(), cnt.data_ptr(), E=E, cap=cap)
+        cnt.fill_(cap - 1)
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    c.close()
+    # SURVEY 8(d): 16 B per seed-step (+8 path length) + the flow field once per frame per kernel
+    by = 16 * n + 8 * W * H + (16 + 8) * W * H + 8 * W * H + 16 * E * (cap - 1) + 8 * W * H
+    fps = steps / (ms * 1e-3)
+    return {"name": "C4 advection", "reference_call_site": "pathlines.cpp:9-46, ripcurrents.cpp:229-231,611-651, Streakline.cpp:22-48",
+            "workload": "per 1080p flow: 1 048 576 pathline seeds (dt 1, 1 it.) + per-pixel particle field (2 073 600 px) + "
+                        "3 495 streaklines x 299 vertices", "value": fps, "unit": "frames/s", "ms_per_step": ms / steps, "steps": steps,
+            "seed_steps_per_s": fps * (n + W * H + E * (cap - 1)),
+            "roofline": {"bound": "hbm", "bytes_per_frame": by, "achieved": round(by * fps / 1e9, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(by * fps / 1e9 / peak, 4)},
+            "clocks": sampler.summary(t0, t1 + 0.05)}
+
+
+def verify_against_oracle(ctx, frames, order, fps, w, h):
+    """Outside every timed region: ONE step of the benched configuration (same context, same batch size -> same kernel
+    selection) from a clean temporal state, through the host-buffer API, checked frame by frame against the CPU oracle on
+    the flows the GPU produced, plus live OpenCV on two pairs.  Raises on any mismatch."""
+    from oracle import oracle as O
+    ctx.wait()
+    ctx.flow_configure_batch(w, h, *PARAMS, fps)         # restart the clip (same parameters: buffers are kept)
+    ctx.hist_reset(); ctx.accumulator_reset(); ctx.window_configure(w, h, WINDOW)
+    seq = np.stack([frames[i] for i in order[:fps + 1]])
+    masks = np.zeros((fps, h, w), np.uint8)
+    ctx.process_frames(seq[:1], 30, masks[:1])
+    k, res = ctx.process_frames(seq[1:], 31, masks)
+    assert k == fps
+    st = O.HistState(); acc = np.zeros(h * w, np.float32)
+    avg = np.zeros(h * w * 2, np.float32); ring = np.zeros((WINDOW, h * w * 2), np.float32)
+    epe = {}
+    try:
+        import cv2
+    except Exception:
+        cv2 = None
+    for i in range(fps):
+        flow = ctx.flow_host_at(fps - 1 - i)
+        if cv2 is not None and i in (0, fps - 1):
+            ref = cv2.calcOpticalFlowFarneback(seq[i], seq[i + 1], None, *PARAMS)
+            d = np.sqrt(((flow - ref) ** 2).sum(-1))
+            cv2.setUseOptimized(False)
+            ref2 = cv2.calcOpticalFlowFarneback(seq[i], seq[i + 1], None, *PARAMS)
+            cv2.setUseOptimized(True)
+            d2 = np.minimum(d, np.sqrt(((flow - ref2) ** 2).sum(-1)))
+            epe["pair_%d" % i] = {"mean": float(d.mean()), "max_to_nearer_cv2_path": float(d2.max())}
+            if not (d.mean() <= 1e-3 and d2.max() <= 1e-2):
+                raise SystemExit("bench.py check FAILED: flow of pair %d differs from OpenCV: %r" % (i, epe))
+        O.histogram(flow, st)
+        up, _, _ = O.thresholds(st)
+        rmask, _, _ = O.classify_accumulate(flow, up, 31 + i, acc)
+        O.window_update(avg, ring[i % WINDOW], flow, WINDOW)
+        if not (res[i].UPPER == up and res[i].histsum == int(st.histsum[0]) and np.array_equal(masks[i], rmask)):
+            raise SystemExit("bench.py check FAILED: aggregation of frame %d differs from the oracle" % i)
+    if not (np.array_equal(ctx.window_get().ravel(), avg) and np.array_equal(ctx.accumulator_get(w, h).ravel(), acc)
+            and np.array_equal(ctx.hist_get()[2], st.hist2d)):
+        raise SystemExit("bench.py check FAILED: window mean / accumulator / histogram differ from the oracle")
+    return {"oracle_match": True, "frames_checked": fps, "last_UPPER": float(res[fps - 1].UPPER),
+            "histsum": int(res[fps - 1].histsum), "epe_vs_cv2": epe or None,
+            "what": "one %d-frame step of the benched configuration re-run from a clean state outside the timed regions: per-frame "
+                    "UPPER, histsum and outmask, final window mean, accumulator and histogram bit-equal to oracle/ on the GPU's "
+                    "flows; flow of the first and last pair within 1e-3 mean / 1e-2 max px of cv2" % fps}
 
 
 class DevArr:
@@ -422,8 +599,21 @@ def run_ours(args, rank, world, local_rank):
                         "api": "rc_submit_frames(%d pinned host frames) -> %d outmasks + threshold records on the host, rc_wait" % (FRAMES_PER_STEP, FRAMES_PER_STEP)},
                 "host_binding": "rank pinned to %d GPU-local cores (NVML affinity)" % ncpu_local if ncpu_local else "none",
                 "gpu_launches": int(launches), "clocks": sampler.summary(t_region0, t_region1 + 0.05), "roofline": roofline, "kernels": kernels,
-                "check": {"last_UPPER": float(h_results[(state["step"] - 1) & 1][FRAMES_PER_STEP - 1].UPPER),
-                          "histsum": int(h_results[(state["step"] - 1) & 1][FRAMES_PER_STEP - 1].histsum)}}
+                "check": None}
+        if not args.no_check:
+            line["check"] = verify_against_oracle(ctx, frames, order, FRAMES_PER_STEP, W, H)
+        if world == 1 and not args.no_secondary:
+            sampler2 = ClockSampler(local_rank); sampler2.start()
+            sec = []
+            for name, ref, (ww, hh, PP, BB, st_) in [
+                    ("C2 Gaussian winsize 10 (the reference's live driver)", "main.cpp:1119,1481", (W, H, (0.5, 2, 10, 3, 15, 1.2, 256), 32, 8)),
+                    ("C2 Gaussian winsize 20", "main.cpp:609,961", (W, H, (0.5, 2, 20, 3, 15, 1.2, 256), 32, 8)),
+                    ("C3 4K 5 layers winsize 21 box", "BASELINE configs[2]", (3840, 2160, (0.5, 4, 21, 3, 15, 1.2, 0), 8, 8)),
+                    ("C3 4K 5 layers winsize 21 Gaussian", "BASELINE configs[2]", (3840, 2160, (0.5, 4, 21, 3, 15, 1.2, 256), 8, 8))]:
+                sec.append(measure_flow_config(torch, dev, stream, name, ref, ww, hh, PP, BB, st_, peak, sampler2))
+            sec.append(measure_advection(torch, dev, stream, 50, peak, sampler2))
+            sampler2.stop()
+            line["secondary"] = sec
         if world == 1 and not args.no_cpu_baseline:
             workers = min(os.cpu_count() or 1, 32)
             v, cores, kind, sample = cpu_leg(args.cpu_pairs or 2, workers)
