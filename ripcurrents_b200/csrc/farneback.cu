@@ -1315,253 +1315,6 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// FAST path, windows of half-width M = 2, 5, 10 -- second formulation of the marching kernel (default; RC_MARCH=1 selects
-// the first one above for A/B measurements).  Same march (64-column strip, 16 rows per step, ring of 16 + 2M horizontally
-// blurred rows, asynchronous staging of the next step), but the two blur passes are arranged for few instructions AND few
-// shared-memory wavefronts -- ncu shows the first formulation at 63-77 % of the issue slots and 57 % of the L1 data pipe
-// (profiles/r02_march.txt), so both had to come down together:
-//   h-blur  item = (row, channel, 8 adjacent pixels): 16-byte loads of the 8 + 2 MA wide window (MA = M rounded up to 4),
-//           Gaussian taps as packed fp32 FMAs (FFMA2, sm_100) on register-aligned pairs -- taps with an even offset
-//           accumulate into the pixel pairs (0,1)(2,3).., taps with an odd offset into the pairs (-1,0)(1,2)..(7,8), the two
-//           partial sums of every pixel are added at the end: 4.5 packed instructions per tap and 8 pixels instead of 8
-//           scalar ones; box windows: one 2M+1 sum + 7 sliding updates;
-//   v-blur  thread = (column pair, channel): the (rows + 2M) ring values of its two columns are read ONCE into registers
-//           (8-byte loads) and every output row is a run of packed FMAs over a sliding register window; the result
-//           overwrites the ring row that has just left every later window (in place: no extra buffer);
-//   solve   thread = (column, 4 rows) as before: five 4-byte loads per pixel, fp32 solve, then either updateMatrices
-//           (coalesced gathers: lanes are consecutive columns) or the flow store (+ histogram).
-// Staged rows are WPA = 64 + 2 MA + 4 floats apart, so the eight items of a quarter-warp (4 pixel groups x 2 rows) hit
-// 32 distinct banks on every 16-byte load.
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
-
-template <int M, bool FUSE, bool BOX, bool FIRST>
-__global__ void __launch_bounds__(256, FUSE ? 3 : 2)
-flow_march2_kernel(FlowArgs a, int mi, int SEG)
-{
-    constexpr int TX = 64, RB = 16, MA = (M + 3) & ~3, WP = TX + 2 * M, WPA = TX + 2 * MA + 4, RING = RB + 2 * M;
-    constexpr int OFF = MA - M;                     // staged index of image column x0 - M
-    constexpr int VH = M >= 8 ? 8 : 16;             // rows per pass of the vertical blur (register window = VH + 2M pairs)
-    extern __shared__ __align__(16) float msm[];
-    float* sRaw = msm;                              // [RB][5][WPA]: staged index e <-> image column x0 - MA + e
-    float* sRing = msm + RB * 5 * WPA;              // [RING][5][TX]
-    __shared__ unsigned int sH[FUSE ? 1 : RC_HIST_CELLS];
-    const int w = a.w, h = a.h, j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    const int x0 = blockIdx.y * TX, y0 = blockIdx.z * SEG;
-    const float* Min = a.M + (size_t)j * a.m_stride + (size_t)mi * 5 * a.plane;
-    const bool do_hist = !FUSE && a.hist_delta != nullptr;
-    if (do_hist) for (int i = tid; i < RC_HIST_CELLS; i += 256) sH[i] = 0;
-    float kk[M + 1];
-#pragma unroll
-    for (int i = 0; i <= M; i++) kk[i] = a.win.k[i];
-    const float eps_unscaled = 1e-3f / (a.win.post_scale * a.win.post_scale);      // post_scale is 1 for Gaussian windows
-    const RView R0 = rview(a.R0(j), a.plane), R1 = rview(a.R1(j), a.plane);
-    const int nout = min(SEG, h - y0), total = nout + 2 * M;          // staged row s <-> image row y0 - M + s (clamped)
-    int ns = 0, no = 0;
-    const bool interior_x = x0 - M >= 0 && x0 - M + WP <= w;
-    const float2* coarse = FIRST && a.coarse ? reinterpret_cast<const float2*>(a.coarse + (size_t)j * a.coarse_stride) : nullptr;
-    auto stage = [&](int first, int cnt) {
-        if constexpr (FIRST) {
-            constexpr int NQ = (WP + 31) / 32;
-            int xs[NQ], csx[NQ]; float cfx[NQ];
-#pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                xs[q] = clampi(x0 - M + lane + 32 * q, 0, w - 1);
-                csx[q] = 0; cfx[q] = 0.f;
-                if (coarse) resize_coef(xs[q], a.cw, a.sxs, csx[q], cfx[q]);
-            }
-            for (int r = wrp; r < cnt; r += 8) {
-                const int y = clampi(y0 - M + first + r, 0, h - 1);
-                int csy = 0; float cfy = 0.f;
-                if (coarse) resize_coef(y, a.ch, a.sys, csy, cfy);
-#pragma unroll
-                for (int q = 0; q < NQ; q++) {
-                    const int rx = lane + 32 * q;
-                    if (rx < WP) {
-                        float2 fi = make_float2(0.f, 0.f);
-                        if (coarse) fi = upsample_flow_tab(coarse, a.cw, a.ch, csx[q], cfx[q], csy, cfy, a.fscale);
-                        float mm[5];
-                        update_matrices_core<false>(xs[q], y, fi.x, fi.y, w, h, R0, R1, a.pitch, mm);
-#pragma unroll
-                        for (int c = 0; c < 5; c++) sRaw[(r * 5 + c) * WPA + OFF + rx] = mm[c];
-                    }
-                }
-            }
-        } else {
-            // 4- and 8-byte asynchronous copies: ncu charges a 16-byte LDGSTS ~2.8x the L1 wavefronts per byte of these
-            for (int rc = wrp; rc < cnt * 5; rc += 8) {
-                const int r = rc / 5, c = rc - 5 * r;
-                const float* grow = Min + (size_t)c * a.plane + (size_t)clampi(y0 - M + first + r, 0, h - 1) * a.pitch;
-                float* dst = sRaw + rc * WPA + OFF;
-                if (M % 2 == 0 && interior_x) {
-#pragma unroll
-                    for (int q = 0; q < (WP / 2 + 31) / 32; q++) {
-                        const int rx = lane + 32 * q;
-                        if (rx < WP / 2) __pipeline_memcpy_async(dst + 2 * rx, grow + (x0 - M) + 2 * rx, 8);
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < (WP + 31) / 32; q++) {
-                        const int rx = lane + 32 * q;
-                        if (rx < WP) __pipeline_memcpy_async(dst + rx, grow + clampi(x0 - M + rx, 0, w - 1), 4);
-                    }
-                }
-            }
-            __pipeline_commit();
-        }
-    };
-    if (!FIRST) stage(0, min(RB, total));
-    while (ns < total) {
-        const int cnt = min(RB, total - ns);
-        if (FIRST) stage(ns, cnt); else __pipeline_wait_prior(0);
-        __syncthreads();
-        // ---- horizontal blur: item = (row, channel, 8 pixels); item bits: [1:0] group low, [2] row/channel low, [3] group high
-        for (int it = tid; it < ((cnt * 5 + 1) >> 1) * 16; it += 256) {
-            const int g = (it & 3) | ((it >> 1) & 4), rc = ((it >> 2) & 1) | ((it >> 4) << 1);
-            if (rc >= cnt * 5) continue;
-            const int r = rc / 5, c = rc - 5 * r;
-            constexpr int NW = 8 + 2 * MA;
-            float win[NW];
-#pragma unroll
-            for (int q = 0; q < NW / 4; q++)
-                *reinterpret_cast<float4*>(win + 4 * q) = *reinterpret_cast<const float4*>(sRaw + rc * WPA + 8 * g + 4 * q);
-            float o[8];
-            if (BOX) {
-                float run = win[OFF];
-#pragma unroll
-                for (int i = 1; i <= 2 * M; i++) run += win[OFF + i];
-                o[0] = run;
-#pragma unroll
-                for (int i = 1; i < 8; i++) { run += win[OFF + i + 2 * M] - win[OFF + i - 1]; o[i] = run; }
-            } else {
-                // centre of pixel i = win[MA + i]; tap d in [-M, M] reads win[MA + i + d].  Pairs (win[2p], win[2p+1]) are
-                // register-aligned: even d -> pixel pairs (0,1)..(6,7) (accE), odd d -> pixel pairs (-1,0)..(7,8) (accO)
-                float2 accE[4], accO[5];
-#pragma unroll
-                for (int p = 0; p < 4; p++) accE[p] = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int p = 0; p < 5; p++) accO[p] = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int d = -M; d <= M; d++) {
-                    const float kd = kk[d < 0 ? -d : d];
-                    const float2 k2 = make_float2(kd, kd);
-                    if ((d & 1) == 0) {
-#pragma unroll
-                        for (int p = 0; p < 4; p++)
-                            accE[p] = ffma2(make_float2(win[MA + 2 * p + d], win[MA + 2 * p + 1 + d]), k2, accE[p]);
-                    } else {
-#pragma unroll
-                        for (int p = 0; p < 5; p++)
-                            accO[p] = ffma2(make_float2(win[MA + 2 * p - 1 + d], win[MA + 2 * p + d]), k2, accO[p]);
-                    }
-                }
-#pragma unroll
-                for (int p = 0; p < 4; p++) { o[2 * p] = accE[p].x + accO[p].y; o[2 * p + 1] = accE[p].y + accO[p + 1].x; }
-            }
-            float* dst = sRing + (((ns + r) % RING) * 5 + c) * TX + 8 * g;
-            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
-        }
-        __syncthreads();
-        ns += cnt;
-        if (!FIRST && ns < total) stage(ns, min(RB, total - ns));
-        // ---- vertical blur, in place: ring row (no + i) <- blurred output row no + i (that row has left every later window)
-        const int lim = min(ns - 2 * M, nout);
-        const int nrows = lim - no;                                    // <= RB; <= 0 while the window fills
-        if (tid < 160 && nrows > 0) {
-            const int cp = tid & 31, ch = tid >> 5;                    // channel is warp-uniform
-            float2* colp = reinterpret_cast<float2*>(sRing + ch * TX) + cp;
-            constexpr int RSTR = 5 * TX / 2;                           // ring row stride in float2
-            const int s0 = no % RING;
-#pragma unroll
-            for (int half = 0; half < RB / VH; half++) {
-                const int i0 = half * VH;
-                if (i0 < nrows) {
-                    float2 wv[VH + 2 * M];
-#pragma unroll
-                    for (int t = 0; t < VH + 2 * M; t++) {
-                        int sl = s0 + i0 + t; if (sl >= RING) sl -= RING; if (sl >= RING) sl -= RING;
-                        if (i0 + t < nrows + 2 * M) wv[t] = colp[sl * RSTR];
-                    }
-                    float2 run = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int i = 0; i < VH; i++) {
-                        if (i0 + i < nrows) {
-                            float2 acc;
-                            if (BOX) {
-                                if (i == 0) {
-                                    run = wv[0];
-#pragma unroll
-                                    for (int t = 1; t <= 2 * M; t++) run = fadd2(run, wv[t]);
-                                } else {
-                                    run = fadd2(run, make_float2(wv[i + 2 * M].x - wv[i - 1].x, wv[i + 2 * M].y - wv[i - 1].y));
-                                }
-                                acc = run;
-                            } else {
-                                acc = make_float2(kk[M] * wv[i].x, kk[M] * wv[i].y);
-#pragma unroll
-                                for (int t = 1; t <= 2 * M; t++) {
-                                    const float kt = kk[t < M ? M - t : t - M];
-                                    acc = ffma2(wv[i + t], make_float2(kt, kt), acc);
-                                }
-                            }
-                            int sl = s0 + i0 + i; if (sl >= RING) sl -= RING;
-                            colp[sl * RSTR] = acc;
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // ---- solve (+ updateMatrices | flow store): thread = (column, 4 rows)
-        {
-            const int col = tid & 63, rbk = tid >> 6;
-            const int o0 = no + 4 * rbk;
-            if (o0 < lim) {
-                const int x = x0 + col;
-                int slot = o0 % RING;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int y = y0 + o0 + i;
-                    const bool in = x < w && o0 + i < lim;
-                    float2 f = make_float2(0.f, 0.f);
-                    if (in) {
-                        const float* sp = sRing + slot * 5 * TX + col;
-                        f = solve_fast_unscaled(sp[0], sp[TX], sp[2 * TX], sp[3 * TX], sp[4 * TX], eps_unscaled);
-                    }
-                    slot = slot + 1 == RING ? 0 : slot + 1;
-                    if (FUSE) {
-                        if (in) {
-                            float mm[5];
-                            update_matrices_core<false>(x, y, f.x, f.y, w, h, R0, R1, a.pitch, mm);
-                            float* Mo = a.M + (size_t)j * a.m_stride + (size_t)(mi ^ 1) * 5 * a.plane;
-                            const size_t op = (size_t)y * a.pitch + x;
-#pragma unroll
-                            for (int c = 0; c < 5; c++) Mo[c * a.plane + op] = mm[c];
-                        }
-                    } else {
-                        if (in) reinterpret_cast<float2*>(a.out(j))[(size_t)y * w + x] = f;
-                        if (do_hist) {
-                            const int key = in ? hist_key_fast(f.x, f.y) : -1;
-                            const unsigned peers = __match_any_sync(0xffffffffu, key);
-                            if (key >= 0 && (int)(__ffs(peers) - 1) == lane) atomicAdd(&sH[key], __popc(peers));
-                        }
-                    }
-                }
-            }
-        }
-        no = max(lim, 0);
-    }
-    if (do_hist) {
-        __syncthreads();
-        unsigned int* dst = a.hist_delta + (size_t)j * RC_HIST_CELLS;
-        for (int i = tid; i < RC_HIST_CELLS; i += 256)
-            if (sH[i]) atomicAdd(&dst[i], sH[i]);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
 // FAST path, 3x3 window, register/shuffle formulation of the same fused layer: a WARP owns a 32-column strip
 // (32 - 2*NT useful columns) and marches down a segment of rows.  Lane = column.  The last two rows of M of every
 // iteration level live in registers; the vertical 3-sum is formed from them, the horizontal one with two shuffles
@@ -1780,16 +1533,11 @@ void rc_farneback_init_device(int device)
         const int tiled_max = (int)(sizeof(float) * ((size_t)(16 + 32) * (64 + 32) + 16 * (size_t)(64 + 32)));
         cudaFuncSetAttribute(flow_iter_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled_max);
         cudaFuncSetAttribute(flow_iter_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled_max);
-        const int big = (int)(sizeof(float) * (16 * 5 * 92 + 36 * 5 * 64));
+        const int big = (int)(sizeof(float) * (16 * 5 * 84 + 36 * 5 * 64));
 #define RC_CFG1(MM, FU, BX) \
     cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
     cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)
 #define RC_CFG(MM) RC_CFG1(MM, true, true); RC_CFG1(MM, true, false); RC_CFG1(MM, false, true); RC_CFG1(MM, false, false)
-        RC_CFG(2); RC_CFG(5); RC_CFG(10);
-#undef RC_CFG1
-#define RC_CFG1(MM, FU, BX) \
-    cudaFuncSetAttribute(flow_march2_kernel<MM, FU, BX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
-    cudaFuncSetAttribute(flow_march2_kernel<MM, FU, BX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)
         RC_CFG(2); RC_CFG(5); RC_CFG(10);
 #undef RC_CFG
 #undef RC_CFG1
@@ -2010,9 +1758,7 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         const int mnseg = (L.h + 127) / 128;
         const int MSEG = march_seg_env > 0 ? march_seg_env : ((L.h + mnseg - 1) / mnseg + 3) & ~3;
         dim3 gm(nb, (L.w + 63) / 64, (L.h + MSEG - 1) / MSEG);
-        static const bool march_old = getenv("RC_MARCH") && atoi(getenv("RC_MARCH")) == 1;      // first formulation, for A/B runs
-        const size_t msm = march_old ? sizeof(float) * (16 * 5 * (size_t)((64 + 2 * m + 3) & ~3) + (size_t)(16 + 2 * m) * 5 * 64)
-                                     : sizeof(float) * (16 * 5 * (size_t)(64 + 2 * ((m + 3) & ~3) + 4) + (size_t)(16 + 2 * m) * 5 * 64);
+        const size_t msm = sizeof(float) * (16 * 5 * (size_t)((64 + 2 * m + 3) & ~3) + (size_t)(16 + 2 * m) * 5 * 64);
         bool hist_fused = false;
         int mi = 0;
         for (int it = 0; it < T; it++) {
@@ -2020,14 +1766,12 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
             if (it < T - 1) {
                 KScope ks(c, K_FLOW_ITER_FUSED, (80.0 + first_extra) * npx);
                 if (spec) {
-#define RC_LAUNCH_K(KERN, MM, FU) \
-    do { if (it == 0) { \
-             if (box) KERN<MM, FU, true, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
-             else KERN<MM, FU, false, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
-         } else if (box) KERN<MM, FU, true, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
-         else KERN<MM, FU, false, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); } while (0)
 #define RC_LAUNCH_M(MM, FU) \
-    do { if (march_old) RC_LAUNCH_K(flow_march_kernel, MM, FU); else RC_LAUNCH_K(flow_march2_kernel, MM, FU); } while (0)
+    do { if (it == 0) { \
+             if (box) flow_march_kernel<MM, FU, true, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
+             else flow_march_kernel<MM, FU, false, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
+         } else if (box) flow_march_kernel<MM, FU, true, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
+         else flow_march_kernel<MM, FU, false, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); } while (0)
                     if (m == 2) RC_LAUNCH_M(2, true); else if (m == 5) RC_LAUNCH_M(5, true); else RC_LAUNCH_M(10, true);
                 } else if (tiled) flow_iter_tiled_kernel<true><<<gt, 256, tsm, c->stream>>>(a, mi);
                 else update_flow_strict_kernel<true><<<g, b, 0, c->stream>>>(a, mi);
@@ -2038,7 +1782,6 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
                     if (m == 2) RC_LAUNCH_M(2, false); else if (m == 5) RC_LAUNCH_M(5, false); else RC_LAUNCH_M(10, false);
                     hist_fused = true;
 #undef RC_LAUNCH_M
-#undef RC_LAUNCH_K
                 } else if (tiled) flow_iter_tiled_kernel<false><<<gt, 256, tsm, c->stream>>>(a, mi);
                 else update_flow_strict_kernel<false><<<g, b, 0, c->stream>>>(a, mi);
             }
