@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs per worker for the CPU legs (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations (C2-Gaussian, C3, C4)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the frame-pair-sharded single-stream measurement")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle check of the benched configuration")
     return ap.parse_args()
 
@@ -162,7 +163,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -345,6 +346,65 @@ def measure_advection(torch, dev, stream, steps, peak, sampler):
             "clocks": sampler.summary(t0, t1 + 0.05)}
 
 
+def measure_sharded_stream(torch, dist, dev, stream, rank, world, steps, frames):
+    """ONE 1080p stream split by frame pair over the ranks (BASELINE configs[4] second half): per super-block
+    every rank computes 32 pairs (33 device-resident frames, one duplicated frame per block edge); per-frame counts are
+    all-gathered for exact thresholds, the window mean is sharded by pixel band (all-to-all of flow bands), accumulators are
+    all-reduced at the end.  Strong scaling: the stream is the same at every N, value = pairs of the stream per second."""
+    from ripcurrents_b200 import Context, capi
+    BS = 32
+    period = 2 * (CLIP_FRAMES - 1)
+    order = (list(range(CLIP_FRAMES)) + list(range(CLIP_FRAMES - 2, 0, -1)))
+    order = order + order[:BS + 2]
+    d_seq = torch.from_numpy(np.stack([frames[i] for i in order])).to(dev)
+    ctx = Context(dev.index)
+    ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        box = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], rank, world)
+    ctx.flow_configure_batch(W, H, *PARAMS, BS + 1)
+    ctx.shard_configure(WINDOW, 0)
+    ppr = [BS] * world
+    st = {"s": 0}
+
+    def step():
+        g = (st["s"] * world + rank) * BS                      # first pair of this rank's run
+        ctx.shard_step(d_seq.data_ptr() + (g % period) * W * H, 31 + g, ppr, count=BS + 1, want_results=False)
+        st["s"] += 1
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    mask, acc, hist = ctx.shard_report(31 + st["s"] * world * BS, want_mask=True, want_acc=True, want_hist=True)
+    pairs_total = int(hist.sum()) // (W * H) if hist is not None else 0
+    ctx.close()
+    del d_seq
+    torch.cuda.empty_cache()
+    return {"value": steps * world * BS / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "scaling": "strong",
+            "ms_per_super_block": ms / steps, "pairs_per_rank_per_super_block": BS, "super_blocks": steps,
+            "workload": "ONE 1920x1080 stream, reference default Farneback parameters + histograms/thresholds/classify + window "
+                        "mean W=%d, sharded by frame pair" % WINDOW,
+            "exchange": "per super-block and rank: ncclAllGather of %d x 1850 u32 per-frame counts; all-to-all (ncclSend/Recv) of the "
+                        "row bands of %d flows (16.6 MB each, (N-1)/N of them leave the rank) to the ranks that own those rows of the "
+                        "window mean; ncclAllReduce of the accumulators at the reporting point" % (BS, BS),
+            "check": {"accumulator_max": float(acc.max()), "mask_calm_fraction": float((mask == 255).mean()),
+                      "pairs_counted_lower_bound": pairs_total}}
+
+
 def verify_against_oracle(ctx, frames, order, fps, w, h):
     """Outside every timed region: ONE step of the benched configuration (same context, same batch size -> same kernel
     selection) from a clean temporal state, through the host-buffer API, checked frame by frame against the CPU oracle on
@@ -445,7 +505,6 @@ def run_ours(args, rank, world, local_rank):
     ctx = Context(local_rank)
     # all work of this rank (kernels, NCCL, timing events) goes to ONE explicit stream
     stream = torch.cuda.Stream(dev)
-    comm_stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
@@ -454,28 +513,22 @@ def run_ours(args, rank, world, local_rank):
     ctx.window_configure(W, H, WINDOW)
 
     shared = {}
-
-    def setup_shared():
-        # shared (all-camera) accumulators for the per-step all-reduce
-        if world > 1 and not shared:
-            p, aw, ah = ctx.accumulator_device()
-            shared["acc"] = torch.as_tensor(DevArr(p, (ah, aw), "<f4"), device=dev)
-            shared["hist"] = torch.as_tensor(DevArr(ctx.hist_device(), (37 * 50,), "<i8"), device=dev)
-            shared["acc_all"] = torch.empty_like(shared["acc"])
-            shared["hist_all"] = torch.empty_like(shared["hist"])
+    if world > 1:
+        # the library's own NCCL communicator (rc_comm_init): the unique id travels over torch.distributed, the collective
+        # itself is the C ABI's rc_allreduce_accumulators -- what a C++ host would call
+        from ripcurrents_b200 import capi as _capi
+        box = [_capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], rank, world)
 
     def allreduce_shared():
-        # snapshot the rank's accumulators on the compute stream, all-reduce the snapshot on a communication stream:
-        # the collective of step s overlaps the kernels of step s+1 (the snapshot of step s+1 waits for it)
-        setup_shared()
-        if "done" in shared:
-            stream.wait_event(shared["done"])
-        shared["acc_all"].copy_(shared["acc"]); shared["hist_all"].copy_(shared["hist"])
-        snap = torch.cuda.Event(); snap.record(stream)
-        with torch.cuda.stream(comm_stream):
-            comm_stream.wait_event(snap)
-            dist.all_reduce(shared["acc_all"]); dist.all_reduce(shared["hist_all"])
-            shared["done"] = torch.cuda.Event(); shared["done"].record(comm_stream)
+        # shared (all-camera) wave-activity map: all-reduce(SUM) of every rank's accumulator and histogram into separate
+        # buffers (each camera keeps its own state), enqueued on the rank's stream behind the step's kernels
+        if not shared:
+            p, aw, ah = ctx.accumulator_device()
+            shared["acc_all"] = torch.empty((ah, aw), dtype=torch.float32, device=dev)
+            shared["hist_all"] = torch.empty((37 * 50,), dtype=torch.int64, device=dev)
+        ctx.allreduce_accumulators(shared["acc_all"].data_ptr(), shared["hist_all"].data_ptr())
 
     def step_device():
         s = state["step"]
@@ -513,8 +566,7 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(steps):
             step_fn()
         ctx.wait()                 # all device->host copies of the region have landed (no-op for the device leg)
-        stream.wait_stream(comm_stream)      # ... and the last all-reduce has finished
-        e1.record(stream)
+        e1.record(stream)          # behind the last all-reduce, which is enqueued on the same stream
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
@@ -618,14 +670,28 @@ def run_ours(args, rank, world, local_rank):
             workers = min(os.cpu_count() or 1, 32)
             v, cores, kind, sample = cpu_leg(args.cpu_pairs or 2, workers)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
-        print(json.dumps(line), flush=True)
     ctx.close()
+    if not args.no_sharded:
+        sh = measure_sharded_stream(torch, dist, dev, stream, rank, world, 6, frames)
+        if rank == 0:
+            line["sharded_stream"] = sh
+    if rank == 0:
+        print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+OUT = sys.stdout
+
+
 def main():
+    global OUT
     args = parse()
+    # the driver reads ONE JSON line from stdout: keep native libraries (NCCL's version banner, ...) off it by pointing fd 1
+    # at stderr for the duration of the run and printing the line to a private duplicate of the real stdout
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -637,7 +703,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)]
         cmd += sys.argv[1:]
-        raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(subprocess.call(cmd, stdout=OUT.fileno()))
     run_ours(args, rank, world, local_rank)
 
 

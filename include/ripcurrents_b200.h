@@ -213,6 +213,48 @@ int rc_batch_hist(rc_ctx* ctx, int nb, int64_t* deltas /* nb * RC_HIST_ROWS * RC
 int rc_aggregate_last(rc_ctx* ctx, int nb, int framecount0, rc_frame_result* results /* nb records or NULL */);
 int rc_accumulator_mask(rc_ctx* ctx, int framecount, uint8_t* outmask /* w*h u8 */);
 
+/* ---- multi-GPU over NCCL / NVLink -------------------------------------------------------------
+ * The reference is a single process on one stream; these entry points have no reference counterpart.  They give a C / C++
+ * host (main.cpp stays C++) both ways of using the 8 GPUs of a box without any Python:
+ *   camera streams on different GPUs:  one context per (GPU, stream), no exchange in the flow;
+ *                                      rc_allreduce_accumulators builds the shared wave-activity map;
+ *   ONE stream split by frame pair:    rc_shard_configure / rc_shard_step / rc_shard_report (below).
+ * NCCL (libnccl.so.2) is loaded at first use with dlopen; without it these calls fail with RC_ERR_UNSUPPORTED and
+ * everything else works.  All collectives are enqueued on the context's stream. */
+#define RC_COMM_ID_BYTES 128
+/* rank 0: a fresh NCCL unique id; the host program hands the 128 bytes to every rank */
+int rc_comm_unique_id(char id[RC_COMM_ID_BYTES]);
+/* collective over all ranks: communicator of `nranks` ranks on this context's device (ncclCommInitRank) */
+int rc_comm_init(rc_ctx* ctx, const char id[RC_COMM_ID_BYTES], int rank, int nranks);
+/* or adopt a communicator the host program already has (nccl_comm is an ncclComm_t; not destroyed by the context) */
+int rc_comm_attach(rc_ctx* ctx, void* nccl_comm, int rank, int nranks);
+int rc_comm_destroy(rc_ctx* ctx);
+/* all-reduce(SUM) of this context's accumulator.x (w*h fp32) and cumulative hist2d (RC_HIST_ROWS*RC_HIST_BINS int64) over
+ * the ranks of nccl_comm (NULL = the context's communicator).  Results go to the device buffers shared_acc / shared_hist,
+ * or in place when NULL.  Both are integer-valued sums: exact in any order. */
+int rc_allreduce_accumulators(rc_ctx* ctx, void* nccl_comm, float* shared_acc, int64_t* shared_hist);
+
+/* One stream sharded by frame pair.  The stream is consumed in SUPER-BLOCKS: rank r takes the r-th run of
+ * pairs_per_rank[r] (<= max_batch) consecutive pairs of each super-block.  Every rank calls rc_shard_step once per
+ * super-block (ranks with no pairs pass count = 0):
+ *   frames        this rank's count = pairs + 1 frames; the first one is the last frame of the preceding run (one duplicated
+ *                 frame per block edge)
+ *   framecount0   the reference loop counter (ripcurrents.cpp:194) of the frame that completes this rank's first pair
+ *   results       pairs records (exact per-frame thresholds: all-gather of per-frame counts + exclusive prefix) or NULL
+ * rc_shard_configure(window_W, owner): window_W > 0 keeps the fp32 sliding-window mean (main.cpp:1143-1153).  Its rounding is
+ * order-dependent PER PIXEL, so the state is sharded by pixel band: rank r owns rows [r h / N, (r+1) h / N) of the mean;
+ * every step each rank hands band r of its flows to rank r (all-to-all over NVLink: (N-1)/N of a rank's own flows out, as
+ * much in, independent of N) and applies the super-block's updates to its band in stream order -- bit-identical to the
+ * sequential pipeline, no serial tail.  rc_shard_window_get is COLLECTIVE (every rank broadcasts its band) and leaves the
+ * whole mean on every rank.  `owner` is reserved (pass 0).  rc_shard_report (collective): all-reduce of the ranks'
+ * accumulators, then outmask (ripcurrents.cpp:424-439) / accumulator.x / the stream's cumulative hist2d, each optional,
+ * host or device. */
+int rc_shard_configure(rc_ctx* ctx, int window_W, int owner);
+int rc_shard_step(rc_ctx* ctx, const uint8_t* frames, size_t step, size_t frame_stride, int count, int framecount0,
+                  const int* pairs_per_rank, rc_frame_result* results);
+int rc_shard_report(rc_ctx* ctx, int framecount, uint8_t* outmask, float* acc_x, int64_t* hist2d);
+int rc_shard_window_get(rc_ctx* ctx, float* avg /* w*h*2 fp32 */);
+
 /* ---- entry points on the reference's own intermediate formats (used by the header-compatible C++ wrappers) ---- */
 /* counting loop of create_histogram (ripcurrents_module.cpp:94-107) on the merged polar image CV_32FC3
  * (angle deg, mag, mag); adds into the context's cumulative counters like rc_polar_hist */

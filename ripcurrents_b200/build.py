@@ -12,13 +12,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libripcurrents_b200.so")
-SOURCES = ["farneback.cu", "aggregate.cu", "advect.cu", "compat.cu", "fields.cu", "diag.cu", "api.cu"]
+SOURCES = ["farneback.cu", "aggregate.cu", "advect.cu", "compat.cu", "fields.cu", "diag.cu", "comm.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall", "-Xptxas", "-v"]
 # farneback.cu holds both arithmetic modes: its strict code is written with __fmul_rn/__fadd_rn intrinsics (never
 # contracted) and its fast code wants FMA contraction; the other files restate reference arithmetic in which every
 # product and sum rounds separately, so they are compiled with contraction off.
-EXTRA = {"farneback.cu": [], "aggregate.cu": ["-fmad=false"], "advect.cu": ["-fmad=false"], "compat.cu": ["-fmad=false"], "fields.cu": ["-fmad=false"], "diag.cu": ["-fmad=false"], "api.cu": ["-fmad=false"]}
+EXTRA = {"farneback.cu": [], "aggregate.cu": ["-fmad=false"], "advect.cu": ["-fmad=false"], "compat.cu": ["-fmad=false"], "fields.cu": ["-fmad=false"], "diag.cu": ["-fmad=false"], "comm.cu": ["-fmad=false"], "api.cu": ["-fmad=false"]}
 
 
 def _nvcc():
@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
         # --cudart shared: the library carries only the runtime symbols it uses (libcudart.so.12 resolves through the
         # rpath below, or is already loaded by torch in the bench / tests)
         cmd = [_nvcc(), "-shared", "--cudart", "shared", "-o", SO] + objs + [
-            "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+            "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-ldl"]
         subprocess.check_call(cmd)
     return SO
 

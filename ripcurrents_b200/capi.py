@@ -26,6 +26,8 @@ SYMBOLS = [
     "rc_subtract_mean", "rc_average_vector", "rc_batch_hist", "rc_aggregate_last", "rc_accumulator_mask", "rc_mask_edges", "rc_ingest_bgr", "rc_submit_frames_bgr", "rc_hist_from_polar", "rc_create_flow", "rc_create_accumulationbuffer", "rc_advect", "rc_streakline_step", "rc_process_frame",
     "rc_particle_fields", "rc_normalize_jet", "rc_ratio_jet", "rc_field_magnitude", "rc_streamline_positions",
     "rc_subtract_mean_magnitude", "rc_vector_to_color", "rc_shear_rate_to_color",
+    "rc_comm_unique_id", "rc_comm_init", "rc_comm_attach", "rc_comm_destroy", "rc_allreduce_accumulators",
+    "rc_shard_configure", "rc_shard_step", "rc_shard_report", "rc_shard_window_get",
 ]
 
 
@@ -41,11 +43,29 @@ class RcError(RuntimeError):
 _lib = None
 
 
+def _prefer_bundled_nccl():
+    """The library dlopens libnccl.so.2 at first multi-GPU use.  Inside a Python process that may import torch LATER, the
+    system libnccl must not be mapped first (same SONAME, older version: torch's own import would then fail on missing
+    symbols), so point RC_NCCL_LIB at the NCCL wheel torch itself uses when it is installed."""
+    if os.environ.get("RC_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            p = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(p):
+                os.environ["RC_NCCL_LIB"] = p
+    except Exception:
+        pass
+
+
 def load():
     """Loads the shared library (no CUDA call is made)."""
     global _lib
     if _lib is not None:
         return _lib
+    _prefer_bundled_nccl()
     if not os.path.exists(SO_PATH):
         raise RcError("%s is missing: run `python -m ripcurrents_b200.build` (there is no CPU fallback)" % SO_PATH)
     lib = C.CDLL(SO_PATH)
@@ -475,6 +495,56 @@ class Context:
 
     def wait(self):
         self._chk(self.lib.rc_wait(self.h))
+
+    # ---- multi-GPU (NCCL inside the library) ----
+    def comm_init(self, uid, rank, nranks):
+        assert len(uid) == 128
+        self._chk(self.lib.rc_comm_init(self.h, C.c_char_p(bytes(uid)), C.c_int(rank), C.c_int(nranks)))
+
+    def comm_destroy(self):
+        self._chk(self.lib.rc_comm_destroy(self.h))
+
+    def allreduce_accumulators(self, shared_acc=None, shared_hist=None):
+        """device pointers (ints) or None = in place"""
+        self._chk(self.lib.rc_allreduce_accumulators(self.h, None, _ptr(shared_acc), _ptr(shared_hist)))
+
+    def shard_configure(self, window_W, owner):
+        self._chk(self.lib.rc_shard_configure(self.h, C.c_int(window_W), C.c_int(owner)))
+
+    def shard_step(self, frames, framecount0, pairs_per_rank, count=None, want_results=True):
+        """frames: numpy (pairs+1, h, w) u8 / device pointer (with count) / None for a rank without pairs."""
+        if isinstance(frames, np.ndarray):
+            assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.flags.c_contiguous
+            count = frames.shape[0]
+        count = count or 0
+        ppr = (C.c_int * len(pairs_per_rank))(*pairs_per_rank)
+        nb = max(count - 1, 0)
+        res = (FrameResult * nb)() if (want_results and nb) else None
+        n = self.w * self.h_img
+        rc = self._chk(self.lib.rc_shard_step(self.h, _ptr(frames), C.c_size_t(self.w), C.c_size_t(n), C.c_int(count),
+                                              C.c_int(framecount0), ppr, C.byref(res) if res is not None else None))
+        return rc, res
+
+    def shard_report(self, framecount, want_mask=True, want_acc=True, want_hist=True):
+        mask = np.empty((self.h_img, self.w), np.uint8) if want_mask else None
+        acc = np.empty((self.h_img, self.w), np.float32) if want_acc else None
+        hist = np.empty((HIST_ROWS, HIST_BINS), np.int64) if want_hist else None
+        self._chk(self.lib.rc_shard_report(self.h, C.c_int(framecount), _ptr(mask), _ptr(acc), _ptr(hist)))
+        return mask, acc, hist
+
+    def shard_window_get(self):
+        avg = np.empty((self.h_img, self.w, 2), np.float32)
+        self._chk(self.lib.rc_shard_window_get(self.h, _ptr(avg)))
+        return avg
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, every rank passes it to Context.comm_init)."""
+    buf = C.create_string_buffer(128)
+    rc = load().rc_comm_unique_id(buf)
+    if rc != 0:
+        raise RcError("rc_comm_unique_id failed: %s" % load().rc_error_string(rc).decode())
+    return buf.raw
 
 
 _cudart = None

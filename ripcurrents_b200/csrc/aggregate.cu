@@ -249,6 +249,58 @@ classify_batch_kernel(ClassifyBatch cb, size_t n4, size_t n, const float* __rest
     }
 }
 
+// Sliding-window mean alone (main.cpp:1143-1153) over nb consecutive flows: the mean stays in registers across the batch.
+__global__ void __launch_bounds__(256)
+window_batch_kernel(ClassifyBatch cb, size_t n2, float* __restrict__ avg, float inv_w)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // index of a float2 PAIR (two pixels, 16 bytes)
+    if (i >= n2) return;
+    float4 m = reinterpret_cast<const float4*>(avg)[i];
+    for (int j = 0; j < cb.nb; j++) {
+        const float4 f = __ldcs(reinterpret_cast<const float4*>(cb.flow[j]) + i);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cb.old[j]) o = __ldcs(reinterpret_cast<const float4*>(cb.old[j]) + i);
+        m.x = (m.x - o.x * inv_w) + f.x * inv_w; m.y = (m.y - o.y * inv_w) + f.y * inv_w;
+        m.z = (m.z - o.z * inv_w) + f.z * inv_w; m.w = (m.w - o.w * inv_w) + f.w * inv_w;
+    }
+    reinterpret_cast<float4*>(avg)[i] = m;
+}
+
+__global__ void __launch_bounds__(256)
+window_batch_kernel_px(ClassifyBatch cb, size_t n, float* __restrict__ avg, float inv_w)     // odd image sizes: one pixel per thread
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float2 m = reinterpret_cast<const float2*>(avg)[i];
+    for (int j = 0; j < cb.nb; j++) {
+        const float2 f = reinterpret_cast<const float2*>(cb.flow[j])[i];
+        float2 o = make_float2(0.f, 0.f);
+        if (cb.old[j]) o = reinterpret_cast<const float2*>(cb.old[j])[i];
+        m.x = (m.x - o.x * inv_w) + f.x * inv_w; m.y = (m.y - o.y * inv_w) + f.y * inv_w;
+    }
+    reinterpret_cast<float2*>(avg)[i] = m;
+}
+
+// Sharded stream: gathered = [nranks][B][CELLS] per-frame counts of this super-block (zero rows for frames
+// a rank does not have).  hist_start = global + all frames of lower ranks (what this rank's thresholds start from);
+// hist_global += all frames of all ranks (the stream's counters after this super-block).
+__global__ void shard_prefix_kernel(const unsigned int* __restrict__ gathered, int rank, int nranks, int B,
+                                    unsigned long long* __restrict__ hist_global, unsigned long long* __restrict__ hist_start)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= RC_HIST_CELLS) return;
+    unsigned long long lower = 0, all = 0;
+    for (int r = 0; r < nranks; r++) {
+        unsigned long long s = 0;
+        for (int j = 0; j < B; j++) s += gathered[((size_t)r * B + j) * RC_HIST_CELLS + i];
+        if (r < rank) lower += s;
+        all += s;
+    }
+    const unsigned long long g = hist_global[i];
+    hist_start[i] = g + lower;
+    hist_global[i] = g + all;
+}
+
 __global__ void window_update_kernel(const float* __restrict__ flow, size_t flow_step, int w, int h,
                                      float* __restrict__ slot, float* __restrict__ avg, float inv_w)
 {
@@ -368,6 +420,26 @@ void rc_launch_classify_batch(rc_ctx* c, const ClassifyBatch& cb, int w, int h, 
     KScope ks(c, K_CLASSIFY, ((8.0 + (masks ? 1.0 : 0.0)) * cb.nb + 8.0 * nold + 8.0 + (avg ? 16.0 : 0.0)) * n);
     classify_batch_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, c->stream>>>(cb, n4, n, thr_batch, framecount0, acc, masks,
                                                                               avg, inv, vec ? 1 : 0);
+}
+
+void rc_launch_window_batch(rc_ctx* c, const ClassifyBatch& cb, int w, int h, float* avg, int W)
+{
+    const size_t n = (size_t)w * h;
+    int nold = 0;
+    auto al = [](const void* p) { return (reinterpret_cast<size_t>(p) & 15) == 0; };
+    bool vec = n % 2 == 0 && al(avg);
+    for (int j = 0; j < cb.nb; j++) { nold += cb.old[j] ? 1 : 0; vec = vec && al(cb.flow[j]) && al(cb.old[j]); }
+    KScope ks(c, K_WINDOW, (8.0 * cb.nb + 8.0 * nold + 16.0) * n);
+    const float inv = (float)(1.0 / (double)W);
+    if (vec) window_batch_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, c->stream>>>(cb, n / 2, avg, inv);
+    else window_batch_kernel_px<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(cb, n, avg, inv);
+}
+
+void rc_launch_shard_prefix(rc_ctx* c, const unsigned int* gathered, int rank, int nranks, int B, unsigned long long* hist_global,
+                            unsigned long long* hist_start)
+{
+    KScope ks(c, K_THRESHOLDS, 4.0 * nranks * B * RC_HIST_CELLS);
+    shard_prefix_kernel<<<(RC_HIST_CELLS + 127) / 128, 128, 0, c->stream>>>(gathered, rank, nranks, B, hist_global, hist_start);
 }
 
 void rc_launch_widen_counts(rc_ctx* c, const unsigned int* in, long long* out, size_t n)

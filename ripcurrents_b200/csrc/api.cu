@@ -77,6 +77,7 @@ void sync_all(rc_ctx* c)
     if (c->s_in) cudaStreamSynchronize(c->s_in);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->s_out) cudaStreamSynchronize(c->s_out);
+    rc_comm_fence(c, false);
 }
 
 void free_farneback(rc_ctx* c)
@@ -248,8 +249,11 @@ void prof_drain(rc_ctx* c)
 // in sub-batches of at most B.  Returns the number of flows produced (count, or count-1 when priming).
 // With `aggregate` each sub-batch is followed, in stream order, by thresholds + classify (+ window); the per-frame
 // threshold records / masks go to thr_out / masks_out (device, indexed by produced flow).
-int run_frames(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, int count, bool aggregate,
-               int framecount0, float* thr_out, uint8_t* masks_out)
+// aggregate: 0 = flows only, 1 = flows + per-frame counts + thresholds + classify (+ window), 2 = flows + per-frame counts
+// (left in d_hist_delta; sharded streams).  dst_override (optional): where the layer-0 flow of produced pair j goes instead
+// of the context's flow ring.
+int run_frames(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, int count, int aggregate,
+               int framecount0, float* thr_out, uint8_t* masks_out, float* const* dst_override = nullptr)
 {
     const int w = c->prm.w, h = c->prm.h, B = c->B, nslots = B + 1;
     const size_t n = (size_t)w * h;
@@ -263,9 +267,9 @@ int run_frames(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, 
         const int first = (c->r_base + 1) % nslots;
         rc_launch_expand(c, d_frames + (size_t)done * fstride, step, fstride, nb, first);
         float* dst[RC_MAX_BATCH];
-        for (int j = 0; j < nb; j++) dst[j] = ring_slot(c, c->pairs_done + j);
+        for (int j = 0; j < nb; j++) dst[j] = dst_override ? dst_override[produced + j] : ring_slot(c, c->pairs_done + j);
         rc_launch_flows(c, nb, c->r_base, dst, aggregate ? c->d_hist_delta : nullptr);
-        if (aggregate) {
+        if (aggregate == 1) {
             float* thr = thr_out + (size_t)produced * RC_THR_FLOATS;
             rc_launch_thresholds_batch(c, c->d_hist2d, c->d_hist_delta, nb, thr, c->d_thr);
             ClassifyBatch cb;
@@ -317,6 +321,21 @@ int finish_slot(rc_ctx* c, int slot)
 }
 
 }  // namespace
+
+// ---- helpers shared with comm.cu ----------------------------------------------------------------------------------
+int rc_fail(rc_ctx* c, int code, const char* fmt, const char* detail) { return fail(c, code, fmt, detail); }
+bool rc_is_device_ptr(const void* p) { return is_device_ptr(p); }
+int rc_ensure_aggregate(rc_ctx* c) { return ensure_aggregate(c); }
+int rc_ensure_accumulator(rc_ctx* c, int w, int h) { return ensure_accumulator(c, w, h); }
+float* rc_ring_slot(rc_ctx* c, long long pair) { return ring_slot(c, pair); }
+void rc_fill_results(const float* h_thr, int produced, int first_produced, int count, rc_frame_result* results)
+{
+    fill_results(h_thr, produced, first_produced, count, results);
+}
+int rc_run_frames_hist(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, int count, float* const* dst_override)
+{
+    return run_frames(c, d_frames, step, fstride, count, 2, 0, nullptr, nullptr, dst_override);
+}
 
 // =====================================================================================================
 namespace {
@@ -420,6 +439,8 @@ void rc_destroy(rc_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    rc_comm_destroy(c);
+    rc_comm_fence(c, true);
     free_farneback(c);
     void* bufs[] = {c->d_bgr[0], c->d_bgr[1], c->d_tmp, c->d_tmp2, c->d_diag, c->d_hist2d, c->d_thr, c->d_acc, c->d_cls, c->d_swin_ring, c->d_swin_avg};
     for (void* p : bufs) if (p) cudaFree(p);
@@ -458,6 +479,7 @@ int rc_synchronize(rc_ctx* c)
     CUDA_TRY(c, cudaStreamSynchronize(c->s_in));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->s_out));
+    if (rc_comm_fence(c, false)) return fail(c, RC_ERR_CUDA, "communication stream: %s", cudaGetErrorString(cudaGetLastError()));
     return RC_OK;
 }
 
@@ -598,7 +620,7 @@ int rc_flow_push_batch(rc_ctx* c, const uint8_t* frames, size_t step, size_t fra
     if (flows && count - (c->frames_seen == 0 ? 1 : 0) > c->ring_slots)
         return fail(c, RC_ERR_INVALID, "more flows requested than the flow ring holds%s");
     const long long first_pair = c->pairs_done;
-    int produced = run_frames(c, d, ds, dfs, count, false, 0, nullptr, nullptr);
+    int produced = run_frames(c, d, ds, dfs, count, 0, 0, nullptr, nullptr);
     CHECK_LAUNCH(c);
     if (flows && produced > 0) {
         if (flow_step < (size_t)w * 8) return fail(c, RC_ERR_INVALID, "flow_step too small%s");
@@ -1430,7 +1452,7 @@ static int submit_impl(rc_ctx* c, const uint8_t* frames, size_t step, size_t fra
     const int first_produced = c->frames_seen == 0 ? 1 : 0;
     const bool direct = dev_masks && (count == 1 || mask_stride == n);
     uint8_t* d_masks = outmasks ? (direct ? outmasks + (size_t)first_produced * mask_stride : c->d_masks[slot]) : nullptr;
-    int produced = run_frames(c, d, ds, dfs, count, true, framecount0, c->d_thr_batch[slot], d_masks);
+    int produced = run_frames(c, d, ds, dfs, count, 1, framecount0, c->d_thr_batch[slot], d_masks);
     CHECK_LAUNCH(c);
     CUDA_TRY(c, cudaEventRecord(c->ev_compute[slot], c->stream));
     bool host_out = false;
@@ -1510,6 +1532,8 @@ int rc_wait(rc_ctx* c)
     rc = finish_slot(c, s0 ^ 1); if (rc) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->s_in));
     CUDA_TRY(c, cudaStreamSynchronize(c->s_out));
+    // an overlapped accumulator all-reduce (rc_allreduce_accumulators, out of place) joins the context's stream here
+    if (c->ev_ar_done) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_ar_done, 0));
     return RC_OK;
 }
 

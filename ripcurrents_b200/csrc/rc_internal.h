@@ -143,6 +143,25 @@ struct rc_ctx {
     int acc_w = 0, acc_h = 0;
     uint8_t* d_cls = nullptr;                 // waveclass / waterclass scratch (2 planes) for rc_classify_accumulate
 
+    // multi-GPU (comm.cu): NCCL communicator + state of a stream sharded by frame pair
+    void* nccl = nullptr;                     // ncclComm_t
+    bool own_comm = false;
+    int rank = 0, nranks = 1;
+    unsigned int* d_gather = nullptr;         // [nranks][B][RC_HIST_CELLS] all-gathered per-frame counts
+    unsigned long long* d_hist_global = nullptr;   // cumulative counts of the whole stream through the previous super-block
+    float* d_acc_global = nullptr;            // all-reduced accumulator (reporting copy)
+    int shard_owner = 0, shard_W = 0, shard_slots = 0;
+    long long shard_pairs = 0;                // pairs of the whole stream processed so far
+    float* d_shard_ring = nullptr;            // owner rank: flows of the stream in order, W + nranks*B slots
+    float* d_shard_avg = nullptr;             // owner rank: the sliding-window mean
+    float* d_shard_flows = nullptr;           // this rank's flows of the current / previous super-block: [2][B] full frames
+    cudaStream_t s_comm = nullptr;            // collectives that overlap the compute stream (band exchange + window update,
+                                              // out-of-place accumulator all-reduce); created on first use
+    cudaEvent_t ev_ar_snap = nullptr, ev_ar_done = nullptr;
+    cudaEvent_t ev_flows[2] = {nullptr, nullptr}, ev_comm[2] = {nullptr, nullptr};
+    long long shard_steps = 0;
+    bool shard_configured = false;
+
     // stand-alone window (rc_window_* with caller-provided flows)
     int swin_W = 0, swin_w = 0, swin_h = 0, swin_i = 0;
     float* d_swin_ring = nullptr;
@@ -207,6 +226,24 @@ void rc_launch_acc_mask(rc_ctx* c, const float* acc, size_t n, int framecount, u
 void rc_launch_window_update(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float* slot, float* avg,
                              int W);
 void rc_launch_subtract_mean(rc_ctx* c, float* flow, size_t flow_step, int w, int h, double* d_sums);
+
+// window mean alone over nb consecutive flows (the owner rank of a sharded stream)
+void rc_launch_window_batch(rc_ctx* c, const ClassifyBatch& cb, int w, int h, float* avg, int W);
+// sharded stream: start counters of this rank (global + frames of lower ranks) and the next global counters
+void rc_launch_shard_prefix(rc_ctx* c, const unsigned int* gathered, int rank, int nranks, int B, unsigned long long* hist_global,
+                            unsigned long long* hist_start);
+
+// ---- comm.cu -----------------------------------------------------------------------------------------
+int rc_comm_fence(rc_ctx* c, bool destroy);    // wait for the communication stream (and optionally destroy it)
+
+// ---- api.cu helpers used by comm.cu ------------------------------------------------------------------
+int rc_fail(rc_ctx* c, int code, const char* fmt, const char* detail);
+bool rc_is_device_ptr(const void* p);
+int rc_ensure_aggregate(rc_ctx* c);
+int rc_ensure_accumulator(rc_ctx* c, int w, int h);
+float* rc_ring_slot(rc_ctx* c, long long pair);
+void rc_fill_results(const float* h_thr, int produced, int first_produced, int count, rc_frame_result* results);
+int rc_run_frames_hist(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, int count, float* const* dst_override);
 
 // ---- compat.cu -------------------------------------------------------------------------------------
 void rc_launch_hist_polar(rc_ctx* c, const float* polar, size_t step, int w, int h, unsigned long long* hist2d);
