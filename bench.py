@@ -405,6 +405,50 @@ def measure_sharded_stream(torch, dist, dev, stream, rank, world, steps, frames)
                       "pairs_counted_lower_bound": pairs_total}}
 
 
+def copy_roofline(torch, dist, dev, world, h_frames, h_masks, nbytes, steps):
+    """What the box allows for the e2e leg's transfers alone: every rank copies the SAME bytes per step as step_e2e
+    (nbytes of pinned frames host->device, nbytes of masks device->host) with no kernels -- H2D only, D2H only, and both at
+    once on two streams -- all ranks concurrently.  pairs/s at the copy limit = frames per step / time of the 'both' leg."""
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    hf = h_frames.view(-1)[:nbytes]; hm = h_masks.view(-1)[:nbytes]
+    main = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    out = {}
+    for mode in ("h2d", "d2h", "both"):
+        def once():
+            if mode in ("h2d", "both"):
+                with torch.cuda.stream(s_in):
+                    d_in.copy_(hf, non_blocking=True)
+            if mode in ("d2h", "both"):
+                with torch.cuda.stream(s_out):
+                    hm.copy_(d_out, non_blocking=True)
+        once(); once()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        s_in.wait_event(e0); s_out.wait_event(e0)
+        for _ in range(steps):
+            once()
+        main.wait_stream(s_in); main.wait_stream(s_out)
+        e1.record(main)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        out[mode] = ms / steps
+    gb = nbytes / 1e9
+    return {"bytes_each_way_per_step_per_gpu": nbytes, "ranks_copying_concurrently": world,
+            "h2d_only_GBps_per_gpu": round(gb / (out["h2d"] * 1e-3), 2), "d2h_only_GBps_per_gpu": round(gb / (out["d2h"] * 1e-3), 2),
+            "both_GBps_per_gpu_each_way": round(gb / (out["both"] * 1e-3), 2),
+            "aggregate_GBps_each_way": round(world * gb / (out["both"] * 1e-3), 2), "ms_per_step_both": round(out["both"], 3),
+            "pairs_per_s_at_copy_limit": round(world * FRAMES_PER_STEP / (out["both"] * 1e-3), 1)}
+
+
 def verify_against_oracle(ctx, frames, order, fps, w, h):
     """Outside every timed region: ONE step of the benched configuration (same context, same batch size -> same kernel
     selection) from a clean temporal state, through the host-buffer API, checked frame by frame against the CPU oracle on
@@ -587,6 +631,24 @@ def run_ours(args, rank, world, local_rank):
     t_region1 = time.perf_counter()
     sampler.stop()
 
+    # the same end-to-end leg with bit-packed outmasks (rc_set_mask_format: the reference's mask holds only 0 / 255), and what
+    # the box's host<->device links allow for the u8 leg's transfers alone
+    h_masks_packed = [torch.empty((FRAMES_PER_STEP, H * W // 8), dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    def step_e2e_packed():
+        s = state["step"]
+        ctx.process_frames(h_seq.data_ptr() + (s & 1) * NB, 31 + s * FRAMES_PER_STEP, h_masks_packed[s & 1].data_ptr(),
+                           count=FRAMES_PER_STEP, submit_only=True, results=h_results[s & 1])
+        state["step"] = s + 1
+        if world > 1:
+            allreduce_shared()
+
+    ctx.wait()
+    ctx.set_mask_format(True)
+    ms_e2e_packed, _ = timed(step_e2e_packed, args.steps, max(args.warmup, 3))
+    ctx.set_mask_format(False)
+    copy_rf = copy_roofline(torch, dist, dev, world, h_seq, h_masks[0], NB, max(args.steps // 2, 5))
+
     pairs = FRAMES_PER_STEP * args.steps * world
     value = pairs / (ms_dev * 1e-3)
     e2e_value = pairs / (ms_e2e * 1e-3)
@@ -648,7 +710,13 @@ def run_ours(args, rank, world, local_rank):
                 "config": config_dict(world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": FRAMES_PER_STEP * W * H,
                         "d2h_bytes_per_step": FRAMES_PER_STEP * (W * H + 320), "ms_per_step": ms_e2e / args.steps,
-                        "api": "rc_submit_frames(%d pinned host frames) -> %d outmasks + threshold records on the host, rc_wait" % (FRAMES_PER_STEP, FRAMES_PER_STEP)},
+                        "api": "rc_submit_frames(%d pinned host frames) -> %d outmasks + threshold records on the host, rc_wait" % (FRAMES_PER_STEP, FRAMES_PER_STEP),
+                        "copy_roofline": copy_rf,
+                        "frac_of_copy_limit": round(e2e_value / copy_rf["pairs_per_s_at_copy_limit"], 4),
+                        "packed_masks": {"value": pairs / (ms_e2e_packed * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_packed / args.steps,
+                                         "h2d_bytes_per_step": FRAMES_PER_STEP * W * H,
+                                         "d2h_bytes_per_step": FRAMES_PER_STEP * (W * H // 8 + 320),
+                                         "api": "rc_set_mask_format(RC_MASK_PACKED): the same call, outmasks as 1 bit per pixel"}},
                 "host_binding": "rank pinned to %d GPU-local cores (NVML affinity)" % ncpu_local if ncpu_local else "none",
                 "gpu_launches": int(launches), "clocks": sampler.summary(t_region0, t_region1 + 0.05), "roofline": roofline, "kernels": kernels,
                 "check": None}

@@ -27,7 +27,7 @@ SYMBOLS = [
     "rc_particle_fields", "rc_normalize_jet", "rc_ratio_jet", "rc_field_magnitude", "rc_streamline_positions",
     "rc_subtract_mean_magnitude", "rc_vector_to_color", "rc_shear_rate_to_color",
     "rc_comm_unique_id", "rc_comm_init", "rc_comm_attach", "rc_comm_destroy", "rc_allreduce_accumulators",
-    "rc_shard_configure", "rc_shard_step", "rc_shard_report", "rc_shard_window_get",
+    "rc_shard_configure", "rc_shard_step", "rc_shard_report", "rc_shard_window_get", "rc_set_mask_format",
 ]
 
 
@@ -362,8 +362,9 @@ class Context:
         if results is None and want_results:
             results = (FrameResult * count)()
         fn = self.lib.rc_submit_frames if submit_only else self.lib.rc_process_frames
+        mstride = n // 8 if getattr(self, "_mask_packed", False) else n
         rc = self._chk(fn(self.h, _ptr(frames), C.c_size_t(self.w), C.c_size_t(n), C.c_int(count),
-                          C.c_int(framecount0), _ptr(outmasks), C.c_size_t(n),
+                          C.c_int(framecount0), _ptr(outmasks), C.c_size_t(mstride),
                           C.byref(results) if results is not None else None))
         return rc, results
 
@@ -495,6 +496,10 @@ class Context:
 
     def wait(self):
         self._chk(self.lib.rc_wait(self.h))
+
+    def set_mask_format(self, packed):
+        self._chk(self.lib.rc_set_mask_format(self.h, C.c_int(1 if packed else 0)))
+        self._mask_packed = bool(packed)
 
     # ---- multi-GPU (NCCL inside the library) ----
     def comm_init(self, uid, rank, nranks):

@@ -176,7 +176,7 @@ classify_kernel(const float* __restrict__ flow, size_t flow_step, int w, int h, 
 // 1 B mask written.  (ripcurrents.cpp:376-439 + main.cpp:1143-1153, in the reference's order.)
 __global__ void __launch_bounds__(256)
 classify_batch_kernel(ClassifyBatch cb, size_t n4, size_t n, const float* __restrict__ thr_batch, int framecount0,
-                      float* __restrict__ acc, uint8_t* __restrict__ masks, float* __restrict__ avg, float inv_w, int vec)
+                      float* __restrict__ acc, uint8_t* __restrict__ masks, float* __restrict__ avg, float inv_w, int vec, int packed)
 {
     const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= n4) return;
@@ -231,7 +231,13 @@ classify_batch_kernel(ClassifyBatch cb, size_t n4, size_t n, const float* __rest
                 mean[k].y = (mean[k].y - o[k].y * inv_w) + f[k].y * inv_w;
             }
         }
-        if (masks) {
+        if (masks && packed) {
+            // RC_MASK_PACKED: 1 bit per pixel (1 = calm / 255, 0 = wave), pixel p in bit p & 7 of byte p >> 3; the launcher
+            // guarantees n % 8 == 0, so lanes (2k, 2k+1) hold the two nibbles of one byte and are active together
+            const unsigned nib = (mk[0] ? 1u : 0u) | (mk[1] ? 2u : 0u) | (mk[2] ? 4u : 0u) | (mk[3] ? 8u : 0u);
+            const unsigned other = __shfl_xor_sync(__activemask(), nib, 1);
+            if (!(i4 & 1)) masks[(size_t)j * (n >> 3) + (i4 >> 1)] = (uint8_t)(nib | (other << 4));
+        } else if (masks) {
             uint8_t* mrow = masks + (size_t)j * n;
             if (full) *reinterpret_cast<uchar4*>(mrow + i) = make_uchar4(mk[0], mk[1], mk[2], mk[3]);
             else for (int k = 0; k < 4; k++) if (i + k < n) mrow[i + k] = mk[k];
@@ -408,7 +414,7 @@ void rc_launch_classify(rc_ctx* c, const float* flow, size_t flow_step, int w, i
 }
 
 void rc_launch_classify_batch(rc_ctx* c, const ClassifyBatch& cb, int w, int h, const float* thr_batch, int framecount0,
-                              float* acc, uint8_t* masks, float* avg, int W)
+                              float* acc, uint8_t* masks, float* avg, int W, int packed)
 {
     const size_t n = (size_t)w * h, n4 = (n + 3) / 4;
     const float inv = W > 0 ? (float)(1.0 / (double)W) : 0.f;
@@ -417,9 +423,10 @@ void rc_launch_classify_batch(rc_ctx* c, const ClassifyBatch& cb, int w, int h, 
     auto al = [](const void* p, size_t a) { return (reinterpret_cast<size_t>(p) & (a - 1)) == 0; };
     bool vec = n % 4 == 0 && al(acc, 16) && al(avg, 16) && al(masks, 4);
     for (int j = 0; j < cb.nb && vec; j++) vec = al(cb.flow[j], 16) && al(cb.old[j], 16);
-    KScope ks(c, K_CLASSIFY, ((8.0 + (masks ? 1.0 : 0.0)) * cb.nb + 8.0 * nold + 8.0 + (avg ? 16.0 : 0.0)) * n);
+    if (packed) vec = vec && true;      // packed masks are byte stores: no alignment requirement on `masks`
+    KScope ks(c, K_CLASSIFY, ((8.0 + (masks ? (packed ? 0.125 : 1.0) : 0.0)) * cb.nb + 8.0 * nold + 8.0 + (avg ? 16.0 : 0.0)) * n);
     classify_batch_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, c->stream>>>(cb, n4, n, thr_batch, framecount0, acc, masks,
-                                                                              avg, inv, vec ? 1 : 0);
+                                                                              avg, inv, vec ? 1 : 0, packed);
 }
 
 void rc_launch_window_batch(rc_ctx* c, const ClassifyBatch& cb, int w, int h, float* avg, int W)

@@ -280,9 +280,10 @@ int run_frames(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, 
                 cb.old[j] = (c->win_W > 0 && p - c->win_start >= c->win_W) ? ring_slot(c, p - c->win_W) : nullptr;
             }
             // framecount of a flow = the caller's loop counter of the frame that completed the pair
+            const size_t mbytes = c->mask_format == RC_MASK_PACKED ? n / 8 : n;
             rc_launch_classify_batch(c, cb, w, h, thr, framecount0 + done, c->d_acc,
-                                     masks_out ? masks_out + (size_t)produced * n : nullptr,
-                                     c->win_W > 0 ? c->d_avg : nullptr, c->win_W);
+                                     masks_out ? masks_out + (size_t)produced * mbytes : nullptr,
+                                     c->win_W > 0 ? c->d_avg : nullptr, c->win_W, c->mask_format == RC_MASK_PACKED ? 1 : 0);
         }
         c->r_base = (c->r_base + nb) % nslots;
         c->pairs_done += nb; c->frames_seen += nb;
@@ -1406,7 +1407,11 @@ static int submit_impl(rc_ctx* c, const uint8_t* frames, size_t step, size_t fra
     if (is_bgr && (!frames || src_h < 1 || step < (size_t)src_w * 3 ||
                    (count > 1 && frame_stride < step * (size_t)(src_h - 1) + (size_t)src_w * 3)))
         return fail(c, RC_ERR_INVALID, "bad BGR frame pointer / step / stride%s");
-    if (outmasks && count > 1 && mask_stride < n) return fail(c, RC_ERR_INVALID, "mask_stride too small%s");
+    const bool packed = c->mask_format == RC_MASK_PACKED;
+    if (packed && outmasks && (n % 8 != 0 || w % 8 != 0))
+        return fail(c, RC_ERR_UNSUPPORTED, "RC_MASK_PACKED needs an image width that is a multiple of 8%s");
+    const size_t mb = packed ? n / 8 : n;          // bytes of one outmask
+    if (outmasks && count > 1 && mask_stride < mb) return fail(c, RC_ERR_INVALID, "mask_stride too small%s");
     int rc = ensure_aggregate(c); if (rc) return rc;
     rc = ensure_accumulator(c, w, h); if (rc) return rc;
     const int slot = (int)(c->submitted & 1);
@@ -1450,7 +1455,7 @@ static int submit_impl(rc_ctx* c, const uint8_t* frames, size_t step, size_t fra
     // masks / thresholds of this batch go to staging slot `slot`; its previous D2H must have drained
     CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_out[slot], 0));
     const int first_produced = c->frames_seen == 0 ? 1 : 0;
-    const bool direct = dev_masks && (count == 1 || mask_stride == n);
+    const bool direct = dev_masks && (count == 1 || mask_stride == mb);
     uint8_t* d_masks = outmasks ? (direct ? outmasks + (size_t)first_produced * mask_stride : c->d_masks[slot]) : nullptr;
     int produced = run_frames(c, d, ds, dfs, count, 1, framecount0, c->d_thr_batch[slot], d_masks);
     CHECK_LAUNCH(c);
@@ -1460,11 +1465,11 @@ static int submit_impl(rc_ctx* c, const uint8_t* frames, size_t step, size_t fra
         CUDA_TRY(c, cudaStreamWaitEvent(c->s_out, c->ev_compute[slot], 0));
         if (outmasks && !direct) {
             const cudaMemcpyKind kind = dev_masks ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-            if (count == 1 || mask_stride == n)
-                CUDA_TRY(c, cudaMemcpyAsync(outmasks + (size_t)first_produced * mask_stride, d_masks, n * produced, kind, c->s_out));
+            if (count == 1 || mask_stride == mb)
+                CUDA_TRY(c, cudaMemcpyAsync(outmasks + (size_t)first_produced * mask_stride, d_masks, mb * produced, kind, c->s_out));
             else
                 for (int j = 0; j < produced; j++)
-                    CUDA_TRY(c, cudaMemcpyAsync(outmasks + (size_t)(first_produced + j) * mask_stride, d_masks + (size_t)j * n, n,
+                    CUDA_TRY(c, cudaMemcpyAsync(outmasks + (size_t)(first_produced + j) * mask_stride, d_masks + (size_t)j * mb, mb,
                                                 kind, c->s_out));
             if (!dev_masks) host_out = true;
         }
@@ -1520,6 +1525,15 @@ int rc_ingest_bgr(rc_ctx* c, const uint8_t* bgr, size_t step, int src_w, int src
     CHECK_LAUNCH(c);
     if (hout) CUDA_TRY(c, cudaMemcpy2DAsync(gray, gray_step, d_out, o_step, dst_w, dst_h, cudaMemcpyDeviceToHost, c->stream));
     if (hin || hout) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return RC_OK;
+}
+
+int rc_set_mask_format(rc_ctx* c, int format)
+{
+    if (!c || (format != RC_MASK_U8 && format != RC_MASK_PACKED)) return RC_ERR_INVALID;
+    cudaSetDevice(c->device);
+    sync_all(c);
+    c->mask_format = format;
     return RC_OK;
 }
 

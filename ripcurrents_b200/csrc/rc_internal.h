@@ -81,6 +81,7 @@ struct rc_ctx {
     std::string err;
     std::string launch_err;        // first failed kernel launch since the last CHECK_LAUNCH (kernel class + CUDA error)
     int64_t launches = 0;
+    int mask_format = 0;           // RC_MASK_U8 / RC_MASK_PACKED (rc_set_mask_format)
 
     bool prof_on = false;
     std::vector<ProfRec> prof;
@@ -220,7 +221,7 @@ struct ClassifyBatch {
     int nb;
 };
 void rc_launch_classify_batch(rc_ctx* c, const ClassifyBatch& cb, int w, int h, const float* thr_batch, int framecount0,
-                              float* acc, uint8_t* masks, float* avg, int W);
+                              float* acc, uint8_t* masks, float* avg, int W, int packed = 0);
 void rc_launch_widen_counts(rc_ctx* c, const unsigned int* in, long long* out, size_t n);
 void rc_launch_acc_mask(rc_ctx* c, const float* acc, size_t n, int framecount, uint8_t* mask);
 void rc_launch_window_update(rc_ctx* c, const float* flow, size_t flow_step, int w, int h, float* slot, float* avg,

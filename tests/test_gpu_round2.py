@@ -262,3 +262,36 @@ def test_failed_launch_is_named():
     with pytest.raises(capi.RcError):
         c.advect(flow, seeds, 1.0, 1, 0.0, 99)       # argument errors are caught before any launch
     c.close()
+
+
+def test_packed_outmasks_equal_the_u8_masks():
+    """rc_set_mask_format(RC_MASK_PACKED): bit p & 7 of byte p >> 3 == (u8 mask == 255), through the host-buffer pipeline."""
+    from ripcurrents_b200 import Context, synth
+    w, h, n, B = 320, 200, 9, 4
+    fr = np.stack(synth.clip(w, h, n, seed=33))
+    outs = []
+    for packed in (False, True):
+        c = Context(0)
+        c.flow_configure_batch(w, h, *P_DEFAULT, B); c.hist_reset(); c.window_configure(w, h, 3)
+        c.set_mask_format(packed)
+        per = w * h // 8 if packed else w * h
+        got = []
+        masks = np.zeros((B, per), np.uint8)
+        for lo in range(0, n, B):
+            nb = min(B, n - lo)
+            k, res = c.process_frames(fr[lo:lo + nb], 29 + lo, masks[:nb])
+            for i in range(nb):
+                if res[i].produced:
+                    got.append(masks[i].copy())
+        outs.append(got)
+        c.close()
+    assert len(outs[0]) == len(outs[1]) == n - 1
+    for u8, pk in zip(*outs):
+        assert np.array_equal(np.packbits(u8 == 255, bitorder="little"), pk)
+    assert any((m == 0).any() for m in outs[0]) and any((m == 255).any() for m in outs[0])
+    c = Context(0)
+    c.flow_configure_batch(100, 60, *P_DEFAULT, 2); c.set_mask_format(True)      # 100 % 8 != 0
+    from ripcurrents_b200 import capi
+    with pytest.raises(capi.RcError):
+        c.process_frames(np.zeros((2, 60, 100), np.uint8), 0, np.zeros((2, 750), np.uint8))
+    c.close()
