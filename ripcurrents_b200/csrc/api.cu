@@ -3,6 +3,7 @@
 #include <float.h>
 #include <string.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <new>
 
 #include "rc_internal.h"
@@ -265,7 +266,8 @@ int run_frames(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, 
     while (done < count) {
         const int nb = count - done < B ? count - done : B;
         const int first = (c->r_base + 1) % nslots;
-        rc_launch_expand(c, d_frames + (size_t)done * fstride, step, fstride, nb, first);
+        static const double overlap_max_px = getenv("RC_OVERLAP_MAXPX") ? atof(getenv("RC_OVERLAP_MAXPX")) : 17e6;
+        rc_launch_expand(c, d_frames + (size_t)done * fstride, step, fstride, nb, first, (double)nb * n <= overlap_max_px);
         float* dst[RC_MAX_BATCH];
         for (int j = 0; j < nb; j++) dst[j] = dst_override ? dst_override[produced + j] : ring_slot(c, c->pairs_done + j);
         rc_launch_flows(c, nb, c->r_base, dst, aggregate ? c->d_hist_delta : nullptr);
@@ -423,7 +425,11 @@ int rc_create(rc_ctx** out, int device)
     if (!c) return RC_ERR_NOMEM;
     c->device = device;
     rc_farneback_init_device(device);
-    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+    bool ok = cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_pyr, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_poly[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_poly[1], cudaEventDisableTiming) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) == cudaSuccess;
     for (int s = 0; ok && s < 2; s++)
@@ -454,6 +460,9 @@ void rc_destroy(rc_ctx* c)
     }
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->s_aux) cudaStreamDestroy(c->s_aux);
+    if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
+    for (int i = 0; i < 2; i++) if (c->ev_poly[i]) cudaEventDestroy(c->ev_poly[i]);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

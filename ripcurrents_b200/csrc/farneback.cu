@@ -1574,10 +1574,11 @@ static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
                                                               nslots, c->poly);
 }
 
-void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, int nb, int first_slot)
+void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, int nb, int first_slot, bool overlap)
 {
     const int W = c->prm.w, H = c->prm.h;
     int k_first = 0;
+    c->expand_overlapped = false;
     // layers 0-2 of the default pyramid in one pass over the frame (RC_PYR=separate: one kernel per layer)
     static const bool pyr_fused = !(getenv("RC_PYR") && !strcmp(getenv("RC_PYR"), "separate"));
     if (pyr_fused && c->nlayers >= 3 && W % 4 == 0 && H % 4 == 0 && W >= 16 && H >= 16 && step % 4 == 0 && fstride % 4 == 0 &&
@@ -1598,7 +1599,24 @@ void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fs
             KScope ks(c, K_PYR_V, bytes * nb);
             pyr3_kernel<<<dim3((W + 127) / 128, (H + 31) / 32, nb), 256, 0, c->stream>>>(p);
         }
-        for (int k = 0; k < 3; k++) launch_polyexp(c, c->layer[k], nb, first_slot);
+        if (overlap && c->nlayers == 3 && c->s_aux) {
+            // small batches (frame-by-frame use): the 480x270 and 960x540 layers of one frame do not fill 148 SMs, so the
+            // expansions of layers 1 and 0 run on a second stream while the main stream expands layer 2 and starts the
+            // coarse-to-fine flow; rc_launch_flows waits for ev_poly[k] before the flow of layer k
+            cudaEventRecord(c->ev_pyr, c->stream);
+            cudaStreamWaitEvent(c->s_aux, c->ev_pyr, 0);
+            cudaStream_t keep = c->stream;
+            c->stream = c->s_aux;
+            for (int k = 1; k >= 0; k--) {
+                launch_polyexp(c, c->layer[k], nb, first_slot);
+                cudaEventRecord(c->ev_poly[k], c->s_aux);
+            }
+            c->stream = keep;
+            launch_polyexp(c, c->layer[2], nb, first_slot);
+            c->expand_overlapped = true;
+        } else {
+            for (int k = 0; k < 3; k++) launch_polyexp(c, c->layer[k], nb, first_slot);
+        }
         k_first = 3;
     }
     for (int k = k_first; k < c->nlayers; k++) {
@@ -1683,6 +1701,7 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
     if (hist_delta) cudaMemsetAsync(hist_delta, 0, sizeof(unsigned int) * RC_HIST_CELLS * nb, c->stream);
     for (int k = c->nlayers - 1; k >= 0; k--) {
         Layer& L = c->layer[k];
+        if (c->expand_overlapped && k < 2) cudaStreamWaitEvent(c->stream, c->ev_poly[k], 0);
         FlowArgs a;
         a.R = L.R; a.plane = L.plane; a.pitch = L.pitch; a.w = L.w; a.h = L.h; a.nslots = c->B + 1; a.prev_slot = prev_slot;
         if (k == c->nlayers - 1) { a.coarse = nullptr; a.cw = a.ch = 0; a.coarse_stride = 0; a.sxs = a.sys = 1.0; a.fscale = 1.f; }
@@ -1793,4 +1812,5 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
             hist_batch_kernel<<<dim3(gx, nb), 256, 0, c->stream>>>(a, n);
         }
     }
+    c->expand_overlapped = false;
 }

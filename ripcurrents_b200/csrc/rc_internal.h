@@ -104,6 +104,11 @@ struct rc_ctx {
     int n_flows = 0;               // flows produced by the last push (0..B)
     std::vector<void*> allocs;
 
+    // small-batch overlap: expansions of layers 1/0 on a second stream (rc_launch_expand / rc_launch_flows)
+    cudaStream_t s_aux = nullptr;
+    cudaEvent_t ev_pyr = nullptr, ev_poly[2] = {nullptr, nullptr};
+    bool expand_overlapped = false;
+
     // flow ring: layer-0 flows of the most recent frames; slot of frame-pair index p is p % ring_slots
     float* flow_ring = nullptr;
     int ring_slots = 0;
@@ -199,7 +204,8 @@ struct KScope {
 // ---- farneback.cu ----------------------------------------------------------------------------------
 void rc_farneback_init_device(int device);     // once per device: opt-in shared-memory sizes of the kernels
 // Expands `nb` new frames (device, dense u8, frame stride `fstride`) into R ring slots first_slot.. (mod B+1).
-void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, int nb, int first_slot);
+void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fstride, int nb, int first_slot,
+                      bool overlap = false);
 // Flows for `nb` consecutive pairs: pair j = (ring slot (prev_slot + j) % (B+1), next slot); layer-0 flow of pair j
 // goes to flow_dst[j]; hist_delta (may be null) receives per-pair direction/speed counts [nb][RC_HIST_CELLS].
 void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_host, unsigned int* hist_delta);
