@@ -1206,54 +1206,32 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
         const int cnt = min(RB, total - ns);
         if (FIRST) stage(ns, cnt); else __pipeline_wait_prior(0);
         __syncthreads();
-        // ---- horizontal blur: item = (row, channel, group of 8 pixels).  Gaussian taps as packed fp32 FMAs (FFMA2, sm_100) on
-        // register-aligned pairs of the window: taps whose window offset is even accumulate into the pixel pairs (0,1)(2,3)..,
-        // odd offsets into the pairs (-1,0)(1,2)..(7,8); the two partial sums of a pixel are added at the end -- 4.5 packed
-        // instructions per tap and 8 pixels instead of 8 scalar ones, and half the 16-byte shared loads per pixel of the
-        // 4-pixel items this replaced (ncu: -8 % instructions, -15 % shared wavefronts per launch)
-        for (int it = tid; it < cnt * 5 * (TX / 8); it += 256) {
-            const int xg = it & 7, rc = it >> 3;
+        // ---- horizontal blur: item = (row, channel, group of 4 pixels)
+        for (int it = tid; it < cnt * 5 * (TX / 4); it += 256) {
+            const int xg = it & 15, rc = it >> 4;
             const int r = rc / 5, c = rc - 5 * r;
-            constexpr int NW = (8 + 2 * M + 3) & ~3;
-            float win[NW];
+            float win[4 + 2 * M + 3];
 #pragma unroll
-            for (int q = 0; q < NW / 4; q++)
-                *reinterpret_cast<float4*>(win + 4 * q) = *reinterpret_cast<const float4*>(sRaw + rc * WPA + 8 * xg + 4 * q);
-            float o[8];
+            for (int q = 0; q < (4 + 2 * M + 3) / 4; q++)
+                *reinterpret_cast<float4*>(win + 4 * q) = *reinterpret_cast<const float4*>(sRaw + rc * WPA + 4 * xg + 4 * q);
+            float o[4];
             if (BOX) {
                 float run = win[0];
 #pragma unroll
                 for (int i = 1; i <= 2 * M; i++) run += win[i];
                 o[0] = run;
 #pragma unroll
-                for (int i = 1; i < 8; i++) { run += win[i + 2 * M] - win[i - 1]; o[i] = run; }
+                for (int i = 1; i < 4; i++) { run += win[i + 2 * M] - win[i - 1]; o[i] = run; }
             } else {
-                // pixel i, tap d in [-M, M] reads win[i + M + d]
-                float2 accE[4], accO[5];
 #pragma unroll
-                for (int p = 0; p < 4; p++) accE[p] = make_float2(0.f, 0.f);
+                for (int i = 0; i < 4; i++) {
+                    float v = win[i + M] * kk[0];
 #pragma unroll
-                for (int p = 0; p < 5; p++) accO[p] = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int d = -M; d <= M; d++) {
-                    const float kd = kk[d < 0 ? -d : d];
-                    const float2 k2 = make_float2(kd, kd);
-                    if (((M + d) & 1) == 0) {
-#pragma unroll
-                        for (int p = 0; p < 4; p++)
-                            accE[p] = __ffma2_rn(make_float2(win[2 * p + M + d], win[2 * p + 1 + M + d]), k2, accE[p]);
-                    } else {
-#pragma unroll
-                        for (int p = 0; p < 5; p++)
-                            accO[p] = __ffma2_rn(make_float2(win[2 * p - 1 + M + d], win[2 * p + M + d]), k2, accO[p]);
-                    }
+                    for (int k = 1; k <= M; k++) v = fmaf(win[i + M + k] + win[i + M - k], kk[k], v);
+                    o[i] = v;
                 }
-#pragma unroll
-                for (int p = 0; p < 4; p++) { o[2 * p] = accE[p].x + accO[p].y; o[2 * p + 1] = accE[p].y + accO[p + 1].x; }
             }
-            float* dst = sRing + (((ns + r) % RING) * 5 + c) * TX + 8 * xg;
-            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            *reinterpret_cast<float4*>(sRing + (((ns + r) % RING) * 5 + c) * TX + 4 * xg) = make_float4(o[0], o[1], o[2], o[3]);
         }
         __syncthreads();
         ns += cnt;
