@@ -449,6 +449,37 @@ def copy_roofline(torch, dist, dev, world, h_frames, h_masks, nbytes, steps):
             "pairs_per_s_at_copy_limit": round(world * FRAMES_PER_STEP / (out["both"] * 1e-3), 1)}
 
 
+def measure_cpp_dropin(frames):
+    """The SOURCE-COMPATIBLE route: ripcurrents_b200/cpp/demo_main (the reference's legacy frame loop, ripcurrents.cpp:184-439,
+    written against the reference's own entry points) -- one frame per call, every intermediate through a host cv::Mat."""
+    import tempfile
+    from ripcurrents_b200 import build
+    demo = os.path.join(os.path.dirname(build.SO), "demo_main")
+    if not os.path.exists(demo):
+        return {"name": "C++ drop-in loop", "unavailable": "demo_main not built"}
+    n = 14
+    vals = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        raw = os.path.join(tmp, "frames.raw")
+        np.stack(frames[:n]).tofile(raw)
+        for mode in ("--time", "--time-fused"):
+            r = subprocess.run([demo, raw, str(W), str(H), str(n), os.path.join(tmp, "out.bin"), mode], capture_output=True,
+                               text=True, timeout=300)
+            if r.returncode != 0:
+                return {"name": "C++ drop-in loop", "unavailable": "demo_main %s failed: %s" % (mode, r.stderr[-200:])}
+            vals[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+    return {"name": "C++ drop-in loop, frame by frame (cpp/demo_main.cpp = ripcurrents.cpp:184-439)", "unit": UNIT,
+            "value": vals["--time"]["pairs_per_s"],
+            "source_compatible_route": {"value": vals["--time"]["pairs_per_s"], "pairs": vals["--time"]["pairs"],
+                                        "what": "the reference's own call sequence with the reference's signatures: rc::calcOpticalFlowFarneback "
+                                                "+ streamline_field_all + flowToPolar + create_histogram + create_flow + "
+                                                "create_accumulationbuffer; every intermediate (CV_32FC2 flow, three CV_32FC3 images) crosses the "
+                                                "host in a pageable cv::Mat on every call, as in the reference: ~0.4 GB of host copies per "
+                                                "1080p frame"},
+            "one_call_per_frame_route": {"value": vals["--time-fused"]["pairs_per_s"], "pairs": vals["--time-fused"]["pairs"],
+                                         "what": "the same loop with that block replaced by rc_process_frame(frame, framecount, outmask, "
+                                                 "&result): pageable host gray frame in, outmask + thresholds out (INTEGRATION.md section 3)"}}
+
 def verify_against_oracle(ctx, frames, order, fps, w, h):
     """Outside every timed region: ONE step of the benched configuration (same context, same batch size -> same kernel
     selection) from a clean temporal state, through the host-buffer API, checked frame by frame against the CPU oracle on
@@ -732,6 +763,7 @@ def run_ours(args, rank, world, local_rank):
                     ("C3 4K 5 layers winsize 21 Gaussian", "BASELINE configs[2]", (3840, 2160, (0.5, 4, 21, 3, 15, 1.2, 256), 8, 8))]:
                 sec.append(measure_flow_config(torch, dev, stream, name, ref, ww, hh, PP, BB, st_, peak, sampler2))
             sec.append(measure_advection(torch, dev, stream, 50, peak, sampler2))
+            sec.append(measure_cpp_dropin(frames))
             sampler2.stop()
             line["secondary"] = sec
         if world == 1 and not args.no_cpu_baseline:

@@ -274,6 +274,10 @@ int rc_create_accumulationbuffer(rc_ctx* ctx, float* accumulator3, size_t acc_st
  * cv2 4.13.0.  flags: RC_INGEST_GRAY14 selects OpenCV 3.4's 14-bit gray weights (1868/9617/4899) instead of the
  * 15-bit ones of OpenCV 4 (3735/19235/9798). */
 #define RC_INGEST_GRAY14 1
+/* RC_INGEST_AREA: cv::resize(..., INTER_AREA) instead of INTER_LINEAR -- what the reference applies to the PRIMING frame of
+ * every loop (ripcurrents.cpp:186, main.cpp:223,570,704,936,1067,1429) before cvtColor; downscaling only (both ratios >= 1,
+ * RC_ERR_UNSUPPORTED otherwise), bit-exact against cv2 4.13.0 on fractional, integer and 2x2 ratios. */
+#define RC_INGEST_AREA 2
 int rc_ingest_bgr(rc_ctx* ctx, const uint8_t* bgr, size_t step, int src_w, int src_h, uint8_t* gray, size_t gray_step,
                   int dst_w, int dst_h, int flags);
 /* rc_submit_frames fed with BGR camera frames of any size: H2D of the BGR frames, ingest on the device to the

@@ -216,6 +216,18 @@ def ingest_bgr(bgr, dw, dh, legacy14=False):
     return out
 
 
+def ingest_bgr_area(bgr, dw, dh, legacy14=False):
+    """resize(INTER_AREA) + cvtColor(BGR2GRAY) of the PRIMING frame (ripcurrents.cpp:186-187); downscaling only."""
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    sh, sw, _ = bgr.shape
+    out = np.empty((dh, dw), np.uint8)
+    rc = lib().rc_oracle_ingest_bgr_area(_p(bgr), C.c_size_t(sw * 3), C.c_int(sw), C.c_int(sh), _p(out), C.c_int(dw), C.c_int(dh),
+                                         C.c_int(1 if legacy14 else 0))
+    if rc != 0:
+        raise ValueError("INTER_AREA ingest is restated for downscaling only")
+    return out
+
+
 def edges(mask):
     """create_edges (ripcurrents_module.cpp:216-220): 5x5 elliptical dilate + morphological gradient."""
     mask = np.ascontiguousarray(mask, np.uint8)

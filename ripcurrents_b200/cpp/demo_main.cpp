@@ -3,13 +3,19 @@
 // (calcOpticalFlowFarneback, streamline_field, cartToPolar+merge, create_histogram, create_flow,
 // create_accumulationbuffer) as provided by ripcurrents.hpp of this repository.
 //
-//   demo_main frames.raw W H N out.bin
+//   demo_main frames.raw W H N out.bin [--time]
+// --time: only the hot path of the legacy loop (flow, per-pixel particle field, polar, histogram, create_flow,
+// create_accumulationbuffer), no per-frame record; prints {"pairs_per_s": ...} -- the throughput of the SOURCE-COMPATIBLE
+// route, where every intermediate crosses the host in a cv::Mat exactly as in the reference (bench.py reports it next to the
+// device-resident route)
 // frames.raw: N frames of W*H u8.  out.bin: per processed frame { float UPPER; int histsum; float acc_sum;
 // int mask_calm; float field_sum; streak checksum; byte sums of the three JET images; density sum;
 // byte sums of vectorToColor / shearRateToColor; sum of the mean-magnitude-centred flow } --
 // tests/test_gpu_cpp_dropin.py compares them with the CPU oracle.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "ripcurrents.hpp"
@@ -21,6 +27,8 @@ int main(int argc, char** argv)
 {
     if (argc < 6) { std::fprintf(stderr, "usage: %s frames.raw W H N out.bin\n", argv[0]); return 2; }
     const int W = std::atoi(argv[2]), H = std::atoi(argv[3]), N = std::atoi(argv[4]);
+    const bool timing = argc > 6 && !std::strcmp(argv[6], "--time");
+    const bool timing_fused = argc > 6 && !std::strcmp(argv[6], "--time-fused");
     std::vector<uchar> raw((size_t)W * H * N);
     FILE* f = std::fopen(argv[1], "rb");
     if (!f || std::fread(raw.data(), 1, raw.size(), f) != raw.size()) { std::fprintf(stderr, "cannot read frames\n"); return 1; }
@@ -40,6 +48,45 @@ int main(int argc, char** argv)
     streaks.push_back(Streakline(Pixel2(W * 0.6f, H * 0.5f)));
 
     Mat f2(H, W, CV_8UC1, raw.data());                                                   // preloaded frame, :184-188
+    if (timing_fused) {
+        // the same loop with the block between video.read and imshow replaced by ONE C-ABI call per frame (INTEGRATION.md
+        // section 3): host gray frame in, outmask + thresholds out, everything else stays on the device
+        rc_ctx* ctx = rc::default_context();
+        if (rc_flow_configure(ctx, W, H, 0.5, 2, 3, 2, 15, 1.2, 0) || rc_hist_reset(ctx)) return 1;
+        Mat outmask = Mat::zeros(Size(W, H), CV_8UC1);
+        rc_frame_result res;
+        rc_process_frame(ctx, raw.data(), W, 28, nullptr, nullptr);
+        rc_process_frame(ctx, raw.data() + (size_t)W * H, W, 29, outmask.data, &res);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int framecount = 2; framecount < N; framecount++)
+            if (rc_process_frame(ctx, raw.data() + (size_t)framecount * W * H, W, framecount + 28, outmask.data, &res) != 1) return 1;
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::printf("{\"pairs_per_s\": %.2f, \"pairs\": %d, \"seconds\": %.4f, \"UPPER\": %g}\n", (N - 2) / sec, N - 2, sec, res.UPPER);
+        std::fclose(out_f);
+        return 0;
+    }
+    if (timing) {
+        Mat current, polar;
+        auto body = [&](int framecount) {
+            Mat f1(H, W, CV_8UC1, raw.data() + (size_t)framecount * W * H);
+            rc::calcOpticalFlowFarneback(f2, f1, current, 0.5, 2, 3, 2, 15, 1.2, 0);
+            f2 = f1;
+            rc::streamline_field_all(streamlines_mat, streamlines_distance, current, 2, 1, UPPER);
+            rc::flowToPolar(current, polar);
+            create_histogram(polar, hist, histsum, hist2d, histsum2d, UPPER, UPPER2d, prop_above_upper);
+            Mat accumulator2 = Mat::zeros(Size(W, H), CV_32FC3), waterclass = Mat::zeros(Size(W, H), CV_32FC3);
+            create_flow(polar, waterclass, accumulator2, UPPER, MID, LOWER, UPPER2d);
+            Mat out = Mat::zeros(Size(W, H), CV_32FC3), outmask = Mat::zeros(Size(W, H), CV_8UC1);
+            create_accumulationbuffer(accumulator, accumulator2, out, outmask, framecount + 28);
+        };
+        body(1);                                                                          // warm-up (context, allocations)
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int framecount = 2; framecount < N; framecount++) body(framecount);
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::printf("{\"pairs_per_s\": %.2f, \"pairs\": %d, \"seconds\": %.4f}\n", (N - 2) / sec, N - 2, sec);
+        std::fclose(out_f);
+        return 0;
+    }
     for (int framecount = 1; framecount < N; framecount++) {                             // :194
         Mat f1(H, W, CV_8UC1, raw.data() + (size_t)framecount * W * H);
         Mat current;

@@ -32,8 +32,9 @@ void set_default_device(int device);       // before first use
 // cv::calcOpticalFlowFarneback replacement (ripcurrents.cpp:215, main.cpp:264,609,742,961,1119,1481)
 void calcOpticalFlowFarneback(const cv::Mat& prev, const cv::Mat& next, cv::Mat& flow, double pyr_scale, int levels,
                               int winsize, int iterations, int poly_n, double poly_sigma, int flags);
-// ripcurrents.cpp:209-210: resize(frame, subframe, size, 0, 0, INTER_LINEAR) + cvtColor(subframe, gray, COLOR_BGR2GRAY)
-void ingest(const cv::Mat& frame_bgr, cv::Mat& gray, cv::Size size);
+// ripcurrents.cpp:209-210: resize(frame, subframe, size, 0, 0, INTER_LINEAR) + cvtColor(subframe, gray, COLOR_BGR2GRAY);
+// area = true: the PRIMING frame's resize(..., INTER_AREA) of ripcurrents.cpp:186-187 (downscaling only)
+void ingest(const cv::Mat& frame_bgr, cv::Mat& gray, cv::Size size, bool area = false);
 // ripcurrents.cpp:305-309: split + cartToPolar(deg) + merge -> CV_32FC3 (angle, mag, mag)
 void flowToPolar(const cv::Mat& flow, cv::Mat& polar);
 // whole-image forms of the per-pixel / per-seed loops

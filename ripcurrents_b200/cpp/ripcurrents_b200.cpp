@@ -61,12 +61,12 @@ void calcOpticalFlowFarneback(const cv::Mat& prev, const cv::Mat& next, cv::Mat&
           "rc_farneback");
 }
 
-void ingest(const cv::Mat& frame_bgr, cv::Mat& gray, cv::Size size)
+void ingest(const cv::Mat& frame_bgr, cv::Mat& gray, cv::Size size, bool area)
 {
     require(frame_bgr.type() == CV_8UC3 && size.width > 0 && size.height > 0, "ingest: CV_8UC3 frame required");
     if (gray.rows != size.height || gray.cols != size.width || gray.type() != CV_8UC1) gray.create(size.height, size.width, CV_8UC1);
     check(rc_ingest_bgr(default_context(), frame_bgr.data, frame_bgr.step, frame_bgr.cols, frame_bgr.rows, gray.data, gray.step,
-                        size.width, size.height, 0), "rc_ingest_bgr");
+                        size.width, size.height, area ? RC_INGEST_AREA : 0), "rc_ingest_bgr");
 }
 
 void flowToPolar(const cv::Mat& flow, cv::Mat& polar)

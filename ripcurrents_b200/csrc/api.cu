@@ -1444,8 +1444,10 @@ static int submit_impl(rc_ctx* c, const uint8_t* frames, size_t step, size_t fra
             CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_in[slot], 0));
             d_src = reinterpret_cast<const uint8_t*>(c->d_bgr[slot]); sstep = row; sfs = per;
         }
+        if ((ingest_flags & RC_INGEST_AREA) && (src_w < w || src_h < h))
+            return fail(c, RC_ERR_UNSUPPORTED, "RC_INGEST_AREA is built for downscaling only%s");
         rc_launch_ingest_bgr(c, d_src, sstep, sfs, src_w, src_h, c->d_frames[slot], w, n, w, h, count,
-                             (ingest_flags & RC_INGEST_GRAY14) ? 1 : 0);
+                             (ingest_flags & RC_INGEST_GRAY14) ? 1 : 0, (ingest_flags & RC_INGEST_AREA) ? 1 : 0);
         d = c->d_frames[slot]; ds = w; dfs = n;
     } else if (!dev_in) {
         // H2D on the copy-in stream; it may only overwrite the staging slot once the kernels that read it are done
@@ -1530,7 +1532,10 @@ int rc_ingest_bgr(rc_ctx* c, const uint8_t* bgr, size_t step, int src_w, int src
         int rc = ensure(c, &c->d_tmp2, &c->d_tmp2_cap, (size_t)dst_w * dst_h); if (rc) return rc;
         d_out = reinterpret_cast<uint8_t*>(c->d_tmp2); o_step = dst_w;
     }
-    rc_launch_ingest_bgr(c, d_in, d_step, 0, src_w, src_h, d_out, o_step, 0, dst_w, dst_h, 1, (flags & RC_INGEST_GRAY14) ? 1 : 0);
+    if ((flags & RC_INGEST_AREA) && (src_w < dst_w || src_h < dst_h))
+        return fail(c, RC_ERR_UNSUPPORTED, "RC_INGEST_AREA is built for downscaling only%s");
+    rc_launch_ingest_bgr(c, d_in, d_step, 0, src_w, src_h, d_out, o_step, 0, dst_w, dst_h, 1, (flags & RC_INGEST_GRAY14) ? 1 : 0,
+                         (flags & RC_INGEST_AREA) ? 1 : 0);
     CHECK_LAUNCH(c);
     if (hout) CUDA_TRY(c, cudaMemcpy2DAsync(gray, gray_step, d_out, o_step, dst_w, dst_h, cudaMemcpyDeviceToHost, c->stream));
     if (hin || hout) CUDA_TRY(c, cudaStreamSynchronize(c->stream));

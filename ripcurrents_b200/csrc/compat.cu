@@ -3,6 +3,7 @@
 // CV_32FC3 accumulator / class images of ripcurrents.cpp:371-439.  The device-resident pipeline (rc_process_frames)
 // never materialises these; they exist so that create_histogram / create_flow / create_accumulationbuffer can be
 // swapped in one at a time.  Compiled with -fmad=false.
+#include <math.h>
 #include "rc_internal.h"
 
 namespace {
@@ -120,6 +121,69 @@ ingest_bgr_kernel(const uint8_t* __restrict__ bgr, size_t step, size_t fstride, 
     gray[(size_t)y * gstep + x] = (uint8_t)g;
 }
 
+// INTER_AREA ingest (the PRIMING frame of every loop: ripcurrents.cpp:186-187, main.cpp:223,570,...): cv::resize(INTER_AREA)
+// + cvtColor, downscaling only, bit-exact against cv2 4.13.0 (oracle/ingest_oracle.c states the two OpenCV code paths).
+// One thread per destination pixel; the (source index, fp32 weight) entries of its column and row are generated on the fly.
+__device__ __forceinline__ int area_range(int d, int sn, double scale, int& s1, int& s2, float& a_lead, float& a_full, float& a_trail)
+{
+    const double f1 = d * scale, f2 = f1 + scale, cell = fmin(scale, (double)sn - f1);
+    s1 = (int)ceil(f1); s2 = (int)floor(f2);
+    if (s2 > sn - 1) s2 = sn - 1;
+    if (s1 > s2) s1 = s2;
+    a_lead = (s1 - f1 > 1e-3) ? (float)((s1 - f1) / cell) : -1.f;          // < 0: no leading partial cell
+    a_full = (float)(1.0 / cell);
+    a_trail = (f2 - s2 > 1e-3) ? (float)(fmin(fmin(f2 - s2, 1.0), cell) / cell) : -1.f;
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+ingest_bgr_area_kernel(const uint8_t* __restrict__ bgr, size_t step, size_t fstride, int sw, int sh, uint8_t* __restrict__ gray,
+                       size_t gstep, size_t gstride, int dw, int dh, double scale_x, double scale_y, int ix, int iy, int legacy14)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dw || y >= dh) return;
+    bgr += (size_t)blockIdx.z * fstride;
+    gray += (size_t)blockIdx.z * gstride;
+    int px[3];
+    if (ix > 0) {                                   // integer ratios: OpenCV's "area fast" path
+        const float sc = 1.f / (float)(ix * iy);
+        int sum[3] = {0, 0, 0};
+        for (int j = 0; j < iy; j++) {
+            const uint8_t* row = bgr + (size_t)(y * iy + j) * step + 3 * (x * ix);
+            for (int i = 0; i < ix; i++) { sum[0] += row[3 * i]; sum[1] += row[3 * i + 1]; sum[2] += row[3 * i + 2]; }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            int v = (ix == 2 && iy == 2) ? (sum[c] + 2) >> 2 : __float2int_rn((float)sum[c] * sc);
+            px[c] = v > 255 ? 255 : v;
+        }
+    } else {
+        int xs1, xs2, ys1, ys2; float xl, xf, xt, yl, yf, yt;
+        area_range(x, sw, scale_x, xs1, xs2, xl, xf, xt);
+        area_range(y, sh, scale_y, ys1, ys2, yl, yf, yt);
+        float sum[3] = {0.f, 0.f, 0.f};
+        bool first = true;
+        auto do_row = [&](int sy, float beta) {
+            const uint8_t* row = bgr + (size_t)sy * step;
+            float buf[3] = {0.f, 0.f, 0.f};
+            if (xl >= 0.f) { const uint8_t* p = row + 3 * (xs1 - 1); buf[0] = buf[0] + (float)p[0] * xl; buf[1] = buf[1] + (float)p[1] * xl; buf[2] = buf[2] + (float)p[2] * xl; }
+            for (int sx = xs1; sx < xs2; sx++) { const uint8_t* p = row + 3 * sx; buf[0] = buf[0] + (float)p[0] * xf; buf[1] = buf[1] + (float)p[1] * xf; buf[2] = buf[2] + (float)p[2] * xf; }
+            if (xt >= 0.f) { const uint8_t* p = row + 3 * xs2; buf[0] = buf[0] + (float)p[0] * xt; buf[1] = buf[1] + (float)p[1] * xt; buf[2] = buf[2] + (float)p[2] * xt; }
+#pragma unroll
+            for (int c = 0; c < 3; c++) sum[c] = first ? beta * buf[c] : sum[c] + beta * buf[c];
+            first = false;
+        };
+        if (yl >= 0.f) do_row(ys1 - 1, yl);
+        for (int sy = ys1; sy < ys2; sy++) do_row(sy, yf);
+        if (yt >= 0.f) do_row(ys2, yt);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { int v = __float2int_rn(sum[c]); px[c] = v < 0 ? 0 : (v > 255 ? 255 : v); }
+    }
+    const int g = legacy14 ? (px[0] * 1868 + px[1] * 9617 + px[2] * 4899 + (1 << 13)) >> 14
+                           : (px[0] * 3735 + px[1] * 19235 + px[2] * 9798 + (1 << 14)) >> 15;
+    gray[(size_t)y * gstep + x] = (uint8_t)g;
+}
+
 // Mask clean-up: create_edges, ripcurrents_module.cpp:216-220 -- dilate with OpenCV's
 // 5x5 ellipse, then morphological gradient (dilate - erode) with the same element; taps outside the image are ignored.
 // One 32x32 tile per CTA, all stages in shared memory (halo 4), any number of masks per launch (blockIdx.z).
@@ -186,10 +250,18 @@ void rc_launch_edges(rc_ctx* c, const uint8_t* mask, size_t step, size_t stride,
 }
 
 void rc_launch_ingest_bgr(rc_ctx* c, const uint8_t* bgr, size_t step, size_t fstride, int sw, int sh, uint8_t* gray,
-                          size_t gstep, size_t gstride, int dw, int dh, int nb, int legacy14)
+                          size_t gstep, size_t gstride, int dw, int dh, int nb, int legacy14, int area)
 {
     dim3 g((dw + 31) / 32, (dh + 7) / 8, nb);
     KScope ks(c, K_MISC, (3.0 * sw * sh + (double)dw * dh) * nb);
+    if (area) {
+        const double fx = (double)sw / (double)dw, fy = (double)sh / (double)dh;
+        const int ix = (int)nearbyint(fx), iy = (int)nearbyint(fy);
+        const bool fast = fabs(fx - ix) < 2.220446049250313e-16 && fabs(fy - iy) < 2.220446049250313e-16;
+        ingest_bgr_area_kernel<<<g, 256, 0, c->stream>>>(bgr, step, fstride, sw, sh, gray, gstep, gstride, dw, dh, fx, fy,
+                                                        fast ? ix : 0, fast ? iy : 0, legacy14);
+        return;
+    }
     ingest_bgr_kernel<<<g, 256, 0, c->stream>>>(bgr, step, fstride, sw, sh, gray, gstep, gstride, dw, dh,
                                                (double)sw / (double)dw, (double)sh / (double)dh, legacy14);
 }

@@ -260,7 +260,7 @@ void rc_launch_accumulate(rc_ctx* c, float* acc, size_t astep, const float* acc2
                           unsigned char* mask, size_t mstep, int w, int h, int framecount);
 
 void rc_launch_ingest_bgr(rc_ctx* c, const uint8_t* bgr, size_t step, size_t fstride, int sw, int sh, uint8_t* gray,
-                          size_t gstep, size_t gstride, int dw, int dh, int nb, int legacy14);
+                          size_t gstep, size_t gstride, int dw, int dh, int nb, int legacy14, int area = 0);
 
 void rc_launch_edges(rc_ctx* c, const uint8_t* mask, size_t step, size_t stride, int w, int h, uint8_t* out, size_t ostep,
                      size_t ostride, int nb);

@@ -58,6 +58,12 @@ def ingest():
         img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
         g = cv2.cvtColor(cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY)
         out["bgr%d" % i] = img; out["gray%d" % i] = g
+    # the PRIMING frame of every loop is resized with INTER_AREA (ripcurrents.cpp:186): fractional, integer and 2x2 ratios
+    for i, (sw, sh, dw, dh) in enumerate([(480, 270, 160, 120), (300, 200, 128, 96), (256, 192, 128, 96), (384, 288, 128, 96),
+                                          (200, 150, 200, 150)]):
+        img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        g = cv2.cvtColor(cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA), cv2.COLOR_BGR2GRAY)
+        out["area_bgr%d" % i] = img; out["area_gray%d" % i] = g
     np.savez_compressed(os.path.join(HERE, "ingest.npz"), cv2_version=np.array(cv2.__version__), **out)
 
 

@@ -24,6 +24,23 @@ def test_ingest_live(oracle):
         assert np.array_equal(oracle.ingest_bgr(img, dw, dh), ref)
 
 
+def test_ingest_area_golden_and_live(oracle):
+    """the PRIMING frame: resize(INTER_AREA) + cvtColor (ripcurrents.cpp:186-187) -- fixtures, then live cv2 at the
+    reference's own 1080p -> 640x480 (3 x 2.25), a 2x2, a 3x3 and a mixed integer ratio"""
+    z = np.load(os.path.join(GOLDEN, "ingest.npz"))
+    for i in range(5):
+        g = z["area_gray%d" % i]
+        assert np.array_equal(oracle.ingest_bgr_area(z["area_bgr%d" % i], g.shape[1], g.shape[0]), g), i
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    for sw, sh, dw, dh in [(1920, 1080, 640, 480), (1280, 960, 640, 480), (960, 720, 320, 240), (1280, 720, 640, 240), (701, 503, 640, 480)]:
+        img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        ref = cv2.cvtColor(cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA), cv2.COLOR_BGR2GRAY)
+        assert np.array_equal(oracle.ingest_bgr_area(img, dw, dh), ref), (sw, sh, dw, dh)
+    with pytest.raises(ValueError):
+        oracle.ingest_bgr_area(np.zeros((100, 100, 3), np.uint8), 160, 120)
+
+
 def test_edges_vs_cv2(oracle):
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(0)
