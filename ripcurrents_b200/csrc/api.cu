@@ -128,8 +128,9 @@ void make_poly(PolyCoef& pc, int n, double sigma, bool strict)
     pc.n_eff = n;
     if (!strict) {
         // fast mode: drop taps whose x^2-weighted weight is below 1e-9 of the centre weight (invisible in fp32)
+        static const double trunc = getenv("RC_POLY_TRUNC") ? atof(getenv("RC_POLY_TRUNC")) : 1e-9;
         int k = n;
-        while (k > 1 && (double)pc.xxg[k] < 1e-9 * (double)pc.g[0]) k--;
+        while (k > 1 && (double)pc.xxg[k] < trunc * (double)pc.g[0]) k--;
         pc.n_eff = k;
     }
 }
