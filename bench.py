@@ -757,10 +757,10 @@ def run_ours(args, rank, world, local_rank):
             sampler2 = ClockSampler(local_rank); sampler2.start()
             sec = []
             for name, ref, (ww, hh, PP, BB, st_) in [
-                    ("C2 Gaussian winsize 10 (the reference's live driver)", "main.cpp:1119,1481", (W, H, (0.5, 2, 10, 3, 15, 1.2, 256), 32, 8)),
-                    ("C2 Gaussian winsize 20", "main.cpp:609,961", (W, H, (0.5, 2, 20, 3, 15, 1.2, 256), 32, 8)),
-                    ("C3 4K 5 layers winsize 21 box", "BASELINE configs[2]", (3840, 2160, (0.5, 4, 21, 3, 15, 1.2, 0), 8, 8)),
-                    ("C3 4K 5 layers winsize 21 Gaussian", "BASELINE configs[2]", (3840, 2160, (0.5, 4, 21, 3, 15, 1.2, 256), 8, 8))]:
+                    ("C2 Gaussian winsize 10 (the reference's live driver)", "main.cpp:1119,1481", (W, H, (0.5, 2, 10, 3, 15, 1.2, 256), int(os.environ.get("RC_BENCH_SEC_B", "64")), 8)),
+                    ("C2 Gaussian winsize 20", "main.cpp:609,961", (W, H, (0.5, 2, 20, 3, 15, 1.2, 256), int(os.environ.get("RC_BENCH_SEC_B", "64")), 8)),
+                    ("C3 4K 5 layers winsize 21 box", "BASELINE configs[2]", (3840, 2160, (0.5, 4, 21, 3, 15, 1.2, 0), int(os.environ.get("RC_BENCH_SEC_B4K", "16")), 8)),
+                    ("C3 4K 5 layers winsize 21 Gaussian", "BASELINE configs[2]", (3840, 2160, (0.5, 4, 21, 3, 15, 1.2, 256), int(os.environ.get("RC_BENCH_SEC_B4K", "16")), 8))]:
                 sec.append(measure_flow_config(torch, dev, stream, name, ref, ww, hh, PP, BB, st_, peak, sampler2))
             sec.append(measure_advection(torch, dev, stream, 50, peak, sampler2))
             sec.append(measure_cpp_dropin(frames))

@@ -7,7 +7,10 @@ three places, each solved with a tiny exchange:
   cumulative histograms -> thresholds at frame t need the counts of every frame <= t:
         all_gather of per-frame counts (37*50 int64 per frame) + an exclusive prefix over ranks;
   accumulator (plain sum of 0/1 per pixel, frames > 30): all_reduce(SUM) -- integer-valued, exact in any order;
-  outmask: computed from the all-reduced accumulator at the reporting point (block end).
+  outmask: computed from the all-reduced accumulator at the reporting point (block end);
+  sliding-window mean (main.cpp:1143-1153): fp32 and order-dependent, but per pixel -- its state is sharded by ROW BAND:
+        rank r owns rows [r h / N, (r+1) h / N) and receives that band of every flow of the super-block (BandWindow below;
+        the C ABI does this exchange with ncclSend/ncclRecv, csrc/comm.cu).
 
 `backend` abstracts the compute engine so that the same orchestration is exercised on CPU (tests: the oracle, gloo)
 and on GPUs (GpuBackend: the C ABI, NCCL).  Only torch.distributed is used for communication.
@@ -95,6 +98,62 @@ def run_stream(backend, frames, B, framecount_of_pair, dist=None, device=None):
         uppers.update({lo + i: u for i, u in enumerate(res["upper"])})
         base = base + res["counts_total"]
     return {"upper": uppers, "counts_total": base, "accumulator": res["accumulator"] if res else backend.accumulator()}
+
+
+def band_rows(h, world, rank):
+    """Rows [lo, hi) of the window mean owned by `rank` (same split as csrc/comm.cu: r * h // world)."""
+    return rank * h // world, (rank + 1) * h // world
+
+
+class BandWindow:
+    """This rank's row band of the sliding-window flow mean.  update() is called once per super-block with the band of
+    EVERY flow of the super-block, in stream order; `step(avg, slot, flow, W)` is the per-flow arithmetic of
+    main.cpp:1143-1153 (tests pass the oracle's window_update)."""
+
+    def __init__(self, w, h, W, world, rank, step):
+        self.lo, self.hi = band_rows(h, world, rank)
+        self.w, self.W, self.step = w, W, step
+        n = (self.hi - self.lo) * w * 2
+        self.avg = np.zeros(n, np.float32)
+        self.ring = np.zeros((W, n), np.float32)
+        self.count = 0
+
+    def update(self, flow_bands):
+        for f in flow_bands:
+            self.step(self.avg, self.ring[self.count % self.W], np.ascontiguousarray(f, np.float32).reshape(-1), self.W)
+            self.count += 1
+
+
+def exchange_bands(flows, h, dist=None, device=None):
+    """flows: this rank's [n_local, h, w, 2] float32.  Returns the list, in stream order, of THIS rank's row band of every
+    flow of the super-block (all ranks).  torch.distributed has no ragged all-to-all on gloo, so the host-side statement
+    gathers whole flows and slices; the C ABI sends only the bands."""
+    import torch
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    lo, hi = band_rows(h, world, rank)
+    if world == 1:
+        return [f[lo:hi] for f in flows]
+    n_all = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(n_all, torch.tensor([len(flows)], dtype=torch.int64, device=device))
+    n_all = [int(t.item()) for t in n_all]
+    nmax = max(max(n_all), 1)
+    shape = (nmax,) + tuple(flows.shape[1:]) if len(flows) else None
+    shp = [torch.zeros(3, dtype=torch.int64, device=device) for _ in range(world)]
+    mine = torch.tensor(list(flows.shape[1:]) if len(flows) else [0, 0, 0], dtype=torch.int64, device=device)
+    dist.all_gather(shp, mine)
+    hw2 = max((tuple(int(v) for v in t.tolist()) for t in shp), key=lambda t: t[0])
+    pad = np.zeros((nmax,) + hw2, np.float32)
+    if len(flows):
+        pad[:len(flows)] = flows
+    bufs = [torch.zeros((nmax,) + hw2, dtype=torch.float32, device=device) for _ in range(world)]
+    t = torch.from_numpy(pad)
+    dist.all_gather(bufs, t.to(device) if device is not None else t)
+    out = []
+    for r in range(world):
+        b = bufs[r].cpu().numpy()
+        out += [b[j, lo:hi] for j in range(n_all[r])]
+    return out
 
 
 class GpuBackend:

@@ -49,7 +49,18 @@ def _worker(rank, world, port, q, chunked=False):
     w, h, n = 96, 64, 8
     fr = np.stack(synth.clip(w, h, n, seed=3))
     P = (0.5, 1, 3, 2, 5, 1.1, 0)
-    if chunked:      # super-blocks of world * 2 pairs: 7 pairs = two full super-blocks (one ragged) -> three calls
+    if chunked == "window":
+        # the band-sharded window mean next to the aggregation: per super-block of world * 2 pairs every rank computes its
+        # flows, the bands are exchanged, each rank updates its rows in stream order
+        be = OracleBackend(O, P, w, h)
+        win = sharded.BandWindow(w, h, 3, world, rank, O.window_update)
+        n_pairs = n - 1
+        for s0 in range(0, n_pairs, world * 2):
+            lo = min(s0 + rank * 2, n_pairs); hi = min(lo + 2, n_pairs)
+            flows = np.stack([O.farneback(fr[i], fr[i + 1], *P) for i in range(lo, hi)]) if hi > lo else np.zeros((0, h, w, 2), np.float32)
+            win.update(sharded.exchange_bands(flows, h, dist=dist))
+        q.put((rank, win.lo, win.hi, win.avg.copy(), win.count))
+    elif chunked:      # super-blocks of world * 2 pairs: 7 pairs = two full super-blocks (one ragged) -> three calls
         res = sharded.run_stream(OracleBackend(O, P, w, h), fr, 2, lambda p: 28 + p, dist=dist)
         q.put((rank, sorted(res["upper"].items()), res["counts_total"], res["accumulator"]))
     else:
@@ -127,3 +138,31 @@ def test_two_rank_stream_in_super_blocks_matches_sequential(oracle):
     for g in got:
         assert np.array_equal(g[2], st.hist2d)
         assert np.array_equal(g[3], acc)
+
+
+def test_two_rank_band_sharded_window_mean(oracle):
+    """The order-dependent fp32 window mean sharded by row band (what csrc/comm.cu does over NCCL): two ranks, W = 3, a 7-pair
+    clip in super-blocks of 2 x 2 pairs; the two bands put together equal the sequential mean bit for bit."""
+    from ripcurrents_b200 import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + os.getpid() % 40
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, "window")) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=180) for _ in range(2)])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    w, h, n, W = 96, 64, 8, 3
+    fr = np.stack(synth.clip(w, h, n, seed=3))
+    P = (0.5, 1, 3, 2, 5, 1.1, 0)
+    avg = np.zeros(h * w * 2, np.float32); ring = np.zeros((W, h * w * 2), np.float32)
+    for i in range(n - 1):
+        oracle.window_update(avg, ring[i % W], oracle.farneback(fr[i], fr[i + 1], *P), W)
+    avg = avg.reshape(h, w, 2)
+    assert (got[0][1], got[0][2], got[1][1], got[1][2]) == (0, 32, 32, 64)
+    for _, lo, hi, band, count in got:
+        assert count == n - 1
+        assert band.tobytes() == avg[lo:hi].tobytes()
+    assert np.abs(avg).max() > 0
