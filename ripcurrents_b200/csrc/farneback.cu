@@ -18,6 +18,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include "rc_internal.h"
+#include <cuda.h>
 #include <cuda_pipeline.h>
 #include <mutex>
 
@@ -859,6 +860,148 @@ polyexp_packed_kernel(const float* __restrict__ I, size_t istride, int w, int h,
             else
 #pragma unroll
                 for (int i = 0; i < 4; i++) if (x + i < w) R[4 * plane + o + i] = o4v[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Polynomial expansion, FAST kernel, TMA variant (RC_POLYEXP=tma).  Identical arithmetic and identical bits; the only
+// difference is how the (32 + 2 NP) x 128 input tile reaches the SM: ONE cp.async.bulk.tensor.3d (TMA) issued by one thread
+// into shared memory behind an mbarrier, instead of 32 coalesced global loads per thread into registers.  The tensor map
+// describes the layer images [frame][row][column]; coordinates outside the image are zero-filled by the copy engine and
+// never read: the replicate border is resolved when the vertical phase indexes the tile (clamped row / column -> a position
+// inside the tile, because every tile intersects the image).  The tile aliases the memory of the vertical sums, so the
+// occupancy is that of the direct kernel (4 CTAs per SM); measured in profiles/r02_polyexp_variants.txt.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int NP>
+__global__ void __launch_bounds__(256, 4)
+polyexp_tma_kernel(const __grid_constant__ CUtensorMap tmap, int w, int h, int pitch, float* __restrict__ R, size_t plane,
+                   int first_slot, int nslots, PolyCoefF pc)
+{
+    constexpr int TX = 128 - 2 * NP, TY = 32, SW = 128, VB = 16, WIN = VB + 2 * NP, TR = TY + 2 * NP;
+    constexpr unsigned TILE_BYTES = TR * SW * sizeof(float);
+    extern __shared__ __align__(128) unsigned char tsm[];
+    // the input tile ALIASES the first 24.5 KB of the vertical sums: every thread has its column segment in registers before
+    // the first sum is stored (one extra barrier), so the TMA variant needs no more shared memory than the direct one
+    float* tile = reinterpret_cast<float*>(tsm);                                        // [TR][SW]
+    float (*sr)[TY][SW] = reinterpret_cast<float (*)[TY][SW]>(tsm);                      // [3][TY][SW]
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(tsm + 3 * TY * SW * sizeof(float));
+    static_assert(TILE_BYTES <= 3 * TY * SW * sizeof(float), "tile fits under the sums");
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int tid = threadIdx.x;
+    R += (size_t)((first_slot + blockIdx.z) % nslots) * 5 * plane;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(TILE_BYTES) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smem_u32(tile)), "l"(&tmap), "r"(x0 - NP), "r"(y0 - NP), "r"((int)blockIdx.z), "r"(smem_u32(bar))
+                     : "memory");
+    }
+    {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(bar)), "r"(0u) : "memory");
+    }
+    {   // ---- phase V from the shared tile (replicate border = clamped tile coordinates)
+        const int col = tid & 127, seg = tid >> 7;
+        const int cj = clampi(x0 - NP + col, 0, w - 1) - (x0 - NP);
+        const int ybase = y0 + seg * VB - NP;
+        float win[WIN];
+#pragma unroll
+        for (int j = 0; j < WIN; j++) win[j] = tile[(clampi(ybase + j, 0, h - 1) - (y0 - NP)) * SW + cj];
+        __syncthreads();                      // the tile is dead from here on: its memory receives the vertical sums
+#pragma unroll
+        for (int i = 0; i < VB; i++) {
+            float r0 = win[i + NP] * pc.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= NP; k++) {
+                float up = win[i + NP - k], dn = win[i + NP + k];
+                float p = up + dn;
+                r0 = fmaf(pc.g[k], p, r0);
+                r1 = fmaf(pc.xg[k], dn - up, r1);
+                r2 = fmaf(pc.xxg[k], p, r2);
+            }
+            sr[0][seg * VB + i][col] = r0; sr[1][seg * VB + i][col] = r1; sr[2][seg * VB + i][col] = r2;
+        }
+    }
+    __syncthreads();
+    {   // ---- phase H (as polyexp_fast_kernel)
+        constexpr int GPR = TX / 4;
+        constexpr int NW = 4 + 2 * NP;
+        for (int it = tid; it < TY * GPR; it += 256) {
+            const int row = it / GPR, xg4 = it - row * GPR;
+            const int x = x0 + 4 * xg4, y = y0 + row;
+            if (x >= w || y >= h) continue;
+            float wv[NW];
+            float b1[4], b2[4], b4[4], t1[4];
+#pragma unroll
+            for (int j = 0; j < NW / 4; j++)
+                *reinterpret_cast<float4*>(wv + 4 * j) = *reinterpret_cast<const float4*>(&sr[0][row][4 * xg4 + 4 * j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float a1 = wv[NP + i] * pc.g[0], a2 = 0.f, a4 = 0.f;
+#pragma unroll
+                for (int k = 1; k <= NP; k++) {
+                    float p = wv[NP + i + k], m = wv[NP + i - k];
+                    float tg = p + m;
+                    a1 = fmaf(tg, pc.g[k], a1);
+                    a4 = fmaf(tg, pc.xxg[k], a4);
+                    a2 = fmaf(p - m, pc.xg[k], a2);
+                }
+                b1[i] = a1; b2[i] = a2; b4[i] = a4;
+            }
+            float o1[4], o3[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                o1[i] = b2[i] * pc.ig11;
+                t1[i] = b1[i] * pc.ig03;
+                o3[i] = fmaf(b4[i], pc.ig33, t1[i]);
+            }
+            float o2[4];
+#pragma unroll
+            for (int j = 0; j < NW / 4; j++)
+                *reinterpret_cast<float4*>(wv + 4 * j) = *reinterpret_cast<const float4*>(&sr[2][row][4 * xg4 + 4 * j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float a5 = wv[NP + i] * pc.g[0];
+#pragma unroll
+                for (int k = 1; k <= NP; k++) a5 = fmaf(wv[NP + i + k] + wv[NP + i - k], pc.g[k], a5);
+                o2[i] = fmaf(a5, pc.ig33, t1[i]);
+            }
+            float o0[4], o4[4];
+#pragma unroll
+            for (int j = 0; j < NW / 4; j++)
+                *reinterpret_cast<float4*>(wv + 4 * j) = *reinterpret_cast<const float4*>(&sr[1][row][4 * xg4 + 4 * j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float a3 = wv[NP + i] * pc.g[0], a6 = 0.f;
+#pragma unroll
+                for (int k = 1; k <= NP; k++) {
+                    float p = wv[NP + i + k], m = wv[NP + i - k];
+                    a3 = fmaf(p + m, pc.g[k], a3);
+                    a6 = fmaf(p - m, pc.xg[k], a6);
+                }
+                o0[i] = a3 * pc.ig11; o4[i] = a6 * pc.ig55;
+            }
+            const size_t o = (size_t)y * pitch + x;
+            float4* A = reinterpret_cast<float4*>(R) + o;
+            if (x + 3 < w) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) A[i] = make_float4(o0[i], o1[i], o2[i], o3[i]);
+                *reinterpret_cast<float4*>(R + 4 * plane + o) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (x + i < w) { A[i] = make_float4(o0[i], o1[i], o2[i], o3[i]); R[4 * plane + o + i] = o4[i]; }
+            }
         }
     }
 }
@@ -1733,6 +1876,7 @@ void rc_farneback_init_device(int device)
                                                       3 * (size_t)32 * (64 + 2 * RC_MAX_POLY_N)));
         cudaFuncSetAttribute(polyexp_strict_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, strict_max);
         cudaFuncSetAttribute(pyr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(polyexp_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 32 * 128 * 4 + 16);
         const int tiled_max = (int)(sizeof(float) * ((size_t)(16 + 32) * (64 + 32) + 16 * (size_t)(64 + 32)));
         cudaFuncSetAttribute(flow_iter_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled_max);
         cudaFuncSetAttribute(flow_iter_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled_max);
@@ -1757,6 +1901,35 @@ static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
     if (!c->strict && c->poly.n_eff > 4 && c->poly.n_eff <= 6) np = 6;      // taps per side: 4, 6, 8, 12 or 16
     if (np > 16) np = 0;
     static const bool packed = getenv("RC_POLYEXP") && !strcmp(getenv("RC_POLYEXP"), "packed");
+    static const bool use_tma = getenv("RC_POLYEXP") && !strcmp(getenv("RC_POLYEXP"), "tma");
+    if (np == 8 && use_tma) {
+        // tensor map of this layer's images [nb][h][w] (row pitch L.pitch); driver entry point resolved at run time so that
+        // the library keeps linking cudart only
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = [] {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess) fn = nullptr;
+            return reinterpret_cast<EncodeFn>(fn);
+        }();
+        CUtensorMap tm;
+        const cuuint64_t gdim[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)c->B};
+        const cuuint64_t gstr[2] = {(cuuint64_t)L.pitch * 4, (cuuint64_t)L.pitch * L.h * 4};
+        const cuuint32_t box[3] = {128, 32 + 2 * 8, 1}, estr[3] = {1, 1, 1};
+        if (encode && encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, L.I, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+            PolyCoefF pf;
+            for (int i = 0; i <= RC_MAX_POLY_N; i++) { pf.g[i] = c->poly.g[i]; pf.xg[i] = c->poly.xg[i]; pf.xxg[i] = c->poly.xxg[i]; }
+            pf.ig11 = (float)c->poly.ig11; pf.ig03 = (float)c->poly.ig03; pf.ig33 = (float)c->poly.ig33; pf.ig55 = (float)c->poly.ig55;
+            const int TX = 128 - 2 * 8;
+            dim3 g((L.w + TX - 1) / TX, (L.h + 31) / 32, nb);
+            const size_t smem = (size_t)3 * 32 * 128 * 4 + 16;
+            polyexp_tma_kernel<8><<<g, 256, smem, c->stream>>>(tm, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf);
+            return;
+        }
+    }
     if (np && packed && np % 4 == 0) {
         PolyCoefF2 p2;
         for (int i = 0; i <= 16; i++) {
