@@ -19,11 +19,22 @@ def test_fused_layer_variant(kernel):
     assert out.returncode == 0 and "variant ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
-@pytest.mark.parametrize("var,val", [("RC_PYR", "separate"), ("RC_FLOW_KERNEL", "strip")])
+@pytest.mark.parametrize("val", ["tma", "packed"])
+def test_expansion_kernel_variant(val):
+    """The opt-in forms of the polynomial-expansion kernel (RC_POLYEXP=tma: cp.async.bulk.tensor staging; =packed: FFMA2 pair
+    accumulators) pass the same golden / oracle / batched checks as the default."""
+    env = dict(os.environ, RC_POLYEXP=val)
+    out = subprocess.run([sys.executable, os.path.join(HERE, "variant_check.py")], env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0 and "variant ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("var,val", [("RC_PYR", "separate"), ("RC_FLOW_KERNEL", "strip"), ("RC_POLYEXP", "tma")])
 def test_alternative_kernels_give_identical_bits(tmp_path, var, val):
     """pyr3_kernel (layers 0-2 in one pass over the frame) against the per-layer pyramid kernels, and the strip form of
     the fused flow layer (forced on every launch) against the tile form these small launches select by default: same
-    arithmetic, so the flows must agree bit for bit -- results do not depend on the batch size that picks the kernel."""
+    arithmetic, so the flows must agree bit for bit -- results do not depend on the batch size that picks the kernel.
+    The TMA form of the expansion kernel differs from the default only in how its input tile reaches shared memory."""
     import numpy as np
     outs = []
     for mode in ("default", "alt"):
