@@ -65,6 +65,7 @@ def build(force=False, verbose=False):
 CPP = os.path.join(HERE, "cpp")
 CPP_LIB = os.path.join(LIBDIR, "libripcurrents_cpp.so")
 DEMO = os.path.join(LIBDIR, "demo_main")
+DEMO_MULTI = os.path.join(LIBDIR, "demo_multi_gpu")
 
 
 def build_cpp(force=False):
@@ -80,6 +81,10 @@ def build_cpp(force=False):
     if force or not os.path.exists(DEMO) or os.path.getmtime(DEMO) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++14", "-Wall", "-o", DEMO, os.path.join(CPP, "demo_main.cpp"),
                                "-L" + LIBDIR, "-lripcurrents_cpp", "-lripcurrents_b200", "-Wl,-rpath,$ORIGIN"])
+    multi_src = os.path.join(CPP, "demo_multi_gpu.cpp")          # plain C ABI + std::thread: one stream sharded over the GPUs
+    if force or not os.path.exists(DEMO_MULTI) or os.path.getmtime(DEMO_MULTI) < max(os.path.getmtime(multi_src), os.path.getmtime(so)):
+        subprocess.check_call(["g++", "-O2", "-std=c++14", "-Wall", "-pthread", "-o", DEMO_MULTI, multi_src, "-L" + LIBDIR,
+                               "-lripcurrents_b200", "-Wl,-rpath,$ORIGIN"])
     return CPP_LIB, DEMO
 
 

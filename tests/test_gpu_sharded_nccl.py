@@ -140,3 +140,34 @@ def test_two_gpus_equal_sequential():
     for r in res:                                            # the mean is sharded by pixel band and assembled on every rank
         assert r[5].tobytes() == ref["avg"].tobytes()
     assert res[0][3].sum() > 0
+
+
+@pytest.mark.parametrize("ngpus", [1, 2])
+def test_cpp_host_shards_one_stream(tmp_path, ngpus):
+    """cpp/demo_multi_gpu.cpp: a C++ host (std::thread per GPU, the plain C ABI, no Python, no NCCL headers) shards one stream
+    by frame pair; thresholds, accumulator, mask and window mean equal the sequential pipeline bit for bit."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < ngpus:
+        pytest.skip("needs %d GPUs" % ngpus)
+    from ripcurrents_b200 import Context, build
+    build.build_cpp()
+    fr = _clip()
+    ref = _sequential(Context, fr)
+    raw = tmp_path / "frames.raw"; out = tmp_path / "out.bin"
+    fr.tofile(raw)
+    r = subprocess.run([build.DEMO_MULTI, str(raw), str(W_IMG), str(H_IMG), str(NFRAMES), str(ngpus), str(B), str(out)],
+                       capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0 and "demo_multi_gpu ok" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+    blob = open(out, "rb").read()
+    npairs = int(np.frombuffer(blob, np.int32, 1)[0]); off = 4
+    assert npairs == NFRAMES - 1
+    upper = np.frombuffer(blob, np.float32, npairs, off); off += 4 * npairs
+    hsum = np.frombuffer(blob, np.int64, npairs, off); off += 8 * npairs
+    n = W_IMG * H_IMG
+    acc = np.frombuffer(blob, np.float32, n, off); off += 4 * n
+    mask = np.frombuffer(blob, np.uint8, n, off); off += n
+    avg = np.frombuffer(blob, np.float32, 2 * n, off)
+    assert upper.tolist() == [np.float32(u) for u in ref["ups"]] and hsum.tolist() == ref["sums"]
+    assert np.array_equal(acc.reshape(H_IMG, W_IMG), ref["acc"]) and np.array_equal(mask.reshape(H_IMG, W_IMG), ref["mask"])
+    assert avg.tobytes() == ref["avg"].tobytes()
