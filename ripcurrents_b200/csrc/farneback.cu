@@ -1467,11 +1467,13 @@ flow_layer_kernel(FlowArgs a)
 // FIRST: the first iteration of a layer.  M does not exist yet: the staged rows are COMPUTED (flow initialisation from
 // the coarser layer + updateMatrices, at the replicate-clamped pixel) instead of copied, which removes the separate
 // updateMatrices launch and its 20 B/px write + 20 B/px read.
-template <int M, bool FUSE, bool BOX, bool FIRST>
-__global__ void __launch_bounds__(256, FUSE ? 3 : 2)
+// NTHR = 256 (16 rows per step) or 128 (8 rows per step: half the shared memory per CTA, twice the resident CTAs -- more
+// independent phase machines per SM to cover each other's updateMatrices gathers and barriers; RC_MARCH_THREADS)
+template <int M, bool FUSE, bool BOX, bool FIRST, int NTHR>
+__global__ void __launch_bounds__(NTHR, NTHR == 256 ? (FUSE ? 3 : 2) : (FUSE ? 6 : 4))
 flow_march_kernel(FlowArgs a, int mi, int SEG)
 {
-    constexpr int TX = 64, RB = 16, WP = TX + 2 * M, WPA = (WP + 3) & ~3, RING = RB + 2 * M;
+    constexpr int TX = 64, RB = NTHR / 16, NWARP = NTHR / 32, WP = TX + 2 * M, WPA = (WP + 3) & ~3, RING = RB + 2 * M;
     extern __shared__ __align__(16) float msm[];
     float* sRaw = msm;                         // [RB][5][WPA]
     float* sRing = msm + RB * 5 * WPA;         // [RING][5][TX]
@@ -1483,7 +1485,7 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
     const float* Min = a.M + (size_t)j * a.m_stride + (size_t)mi * 5 * a.plane;
     const bool do_hist = !FUSE && a.hist_delta != nullptr;
     if (do_hist) {
-        for (int i = tid; i < RC_HIST_CELLS; i += 256) sH[i] = 0;
+        for (int i = tid; i < RC_HIST_CELLS; i += NTHR) sH[i] = 0;
         if (tid == 0) sNKeys = 0;
     }
     float kk[M + 1];
@@ -1508,7 +1510,7 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
                 csx[q] = 0; cfx[q] = 0.f;
                 if (coarse) resize_coef(xs[q], a.cw, a.sxs, csx[q], cfx[q]);
             }
-            for (int r = wrp; r < cnt; r += 8) {
+            for (int r = wrp; r < cnt; r += NWARP) {
                 const int y = clampi(y0 - M + first + r, 0, h - 1);
                 int csy = 0; float cfy = 0.f;
                 if (coarse) resize_coef(y, a.ch, a.sys, csy, cfy);
@@ -1526,7 +1528,7 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
                 }
             }
         } else {
-            for (int rc = wrp; rc < cnt * 5; rc += 8) {
+            for (int rc = wrp; rc < cnt * 5; rc += NWARP) {
                 const int r = rc / 5, c = rc - 5 * r;
                 const float* grow = Min + (size_t)c * a.plane + (size_t)clampi(y0 - M + first + r, 0, h - 1) * a.pitch;
                 float* dst = sRaw + (r * 5 + c) * WPA;
@@ -1553,7 +1555,7 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
         if (FIRST) stage(ns, cnt); else __pipeline_wait_prior(0);
         __syncthreads();
         // ---- horizontal blur: item = (row, channel, group of 4 pixels)
-        for (int it = tid; it < cnt * 5 * (TX / 4); it += 256) {
+        for (int it = tid; it < cnt * 5 * (TX / 4); it += NTHR) {
             const int xg = it & 15, rc = it >> 4;
             const int r = rc / 5, c = rc - 5 * r;
             float win[4 + 2 * M + 3];
@@ -1652,9 +1654,9 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
         unsigned int* dst = a.hist_delta + (size_t)j * RC_HIST_CELLS;
         const int nk = sNKeys;
         if (nk <= 256) {
-            if (tid < nk) { const int k = sKeys[tid]; atomicAdd(&dst[k], sH[k]); }
+            for (int t = tid; t < nk; t += NTHR) { const int k = sKeys[t]; atomicAdd(&dst[k], sH[k]); }
         } else {
-            for (int i = tid; i < RC_HIST_CELLS; i += 256)
+            for (int i = tid; i < RC_HIST_CELLS; i += NTHR)
                 if (sH[i]) atomicAdd(&dst[i], sH[i]);
         }
     }
@@ -1882,8 +1884,10 @@ void rc_farneback_init_device(int device)
         cudaFuncSetAttribute(flow_iter_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled_max);
         const int big = (int)(sizeof(float) * (16 * 5 * 84 + 36 * 5 * 64));
 #define RC_CFG1(MM, FU, BX) \
-    cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
-    cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)
+    cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
+    cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
+    cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
+    cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)
 #define RC_CFG(MM) RC_CFG1(MM, true, true); RC_CFG1(MM, true, false); RC_CFG1(MM, false, true); RC_CFG1(MM, false, false)
         RC_CFG(2); RC_CFG(5); RC_CFG(10);
 #undef RC_CFG
@@ -2174,6 +2178,11 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         const int MSEG = march_seg_env > 0 ? march_seg_env : ((L.h + mnseg - 1) / mnseg + 3) & ~3;
         dim3 gm(nb, (L.w + 63) / 64, (L.h + MSEG - 1) / MSEG);
         const size_t msm = sizeof(float) * (16 * 5 * (size_t)((64 + 2 * m + 3) & ~3) + (size_t)(16 + 2 * m) * 5 * 64);
+        const size_t msm128 = sizeof(float) * (8 * 5 * (size_t)((64 + 2 * m + 3) & ~3) + (size_t)(8 + 2 * m) * 5 * 64);
+        // 128-thread CTAs (8 rows per step, 35 KB of shared memory, six resident CTAs) for half-widths up to 5: +2.5 % on
+        // Gaussian winsize 10; at half-width 10 the ring alone is 36 KB, only four such CTAs fit and the 256-thread form wins
+        static const int march_threads_env = getenv("RC_MARCH_THREADS") ? atoi(getenv("RC_MARCH_THREADS")) : 0;
+        const int march_threads = march_threads_env ? march_threads_env : (m <= 5 ? 128 : 256);
         bool hist_fused = false;
         int mi = 0;
         for (int it = 0; it < T; it++) {
@@ -2181,12 +2190,14 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
             if (it < T - 1) {
                 KScope ks(c, K_FLOW_ITER_FUSED, (80.0 + first_extra) * npx);
                 if (spec) {
-#define RC_LAUNCH_M(MM, FU) \
+#define RC_LAUNCH_MT(MM, FU, NT, SM) \
     do { if (it == 0) { \
-             if (box) flow_march_kernel<MM, FU, true, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
-             else flow_march_kernel<MM, FU, false, true><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
-         } else if (box) flow_march_kernel<MM, FU, true, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); \
-         else flow_march_kernel<MM, FU, false, false><<<gm, 256, msm, c->stream>>>(a, mi, MSEG); } while (0)
+             if (box) flow_march_kernel<MM, FU, true, true, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG); \
+             else flow_march_kernel<MM, FU, false, true, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG); \
+         } else if (box) flow_march_kernel<MM, FU, true, false, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG); \
+         else flow_march_kernel<MM, FU, false, false, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG); } while (0)
+#define RC_LAUNCH_M(MM, FU) \
+    do { if (march_threads == 128) RC_LAUNCH_MT(MM, FU, 128, msm128); else RC_LAUNCH_MT(MM, FU, 256, msm); } while (0)
                     if (m == 2) RC_LAUNCH_M(2, true); else if (m == 5) RC_LAUNCH_M(5, true); else RC_LAUNCH_M(10, true);
                 } else if (tiled) flow_iter_tiled_kernel<true><<<gt, 256, tsm, c->stream>>>(a, mi);
                 else update_flow_strict_kernel<true><<<g, b, 0, c->stream>>>(a, mi);
@@ -2197,6 +2208,7 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
                     if (m == 2) RC_LAUNCH_M(2, false); else if (m == 5) RC_LAUNCH_M(5, false); else RC_LAUNCH_M(10, false);
                     hist_fused = true;
 #undef RC_LAUNCH_M
+#undef RC_LAUNCH_MT
                 } else if (tiled) flow_iter_tiled_kernel<false><<<gt, 256, tsm, c->stream>>>(a, mi);
                 else update_flow_strict_kernel<false><<<g, b, 0, c->stream>>>(a, mi);
             }
