@@ -551,12 +551,13 @@ struct PolyCoefF {
     float ig11, ig03, ig33, ig55;
 };
 
-template <int NP>
-__global__ void __launch_bounds__(256)
+// TY = 32 rows per CTA (256 threads) or 16 (128 threads: half the shared memory, twice the resident CTAs; RC_POLYEXP_ROWS)
+template <int NP, int TY>
+__global__ void __launch_bounds__(TY * 8)
 polyexp_fast_kernel(const float* __restrict__ I, size_t istride, int w, int h, int pitch, float* __restrict__ R,
                     size_t plane, int first_slot, int nslots, PolyCoefF pc)
 {
-    constexpr int TX = 128 - 2 * NP, TY = 32, SW = 128, VB = 16, WIN = VB + 2 * NP;
+    constexpr int TX = 128 - 2 * NP, SW = 128, VB = 16, WIN = VB + 2 * NP, NTHR = TY * 8;
     __shared__ __align__(16) float sr[3][TY][SW];
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const int tid = threadIdx.x;
@@ -588,7 +589,7 @@ polyexp_fast_kernel(const float* __restrict__ I, size_t istride, int w, int h, i
     {   // ---- phase H
         constexpr int GPR = TX / 4;            // 4-wide groups per row
         constexpr int NW = 4 + 2 * NP;         // window width
-        for (int it = tid; it < TY * GPR; it += 256) {
+        for (int it = tid; it < TY * GPR; it += NTHR) {
             const int row = it / GPR, xg4 = it - row * GPR;
             const int x = x0 + 4 * xg4, y = y0 + row;
             if (x >= w || y >= h) continue;
@@ -1956,14 +1957,22 @@ static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
         for (int i = 0; i <= RC_MAX_POLY_N; i++) { pf.g[i] = c->poly.g[i]; pf.xg[i] = c->poly.xg[i]; pf.xxg[i] = c->poly.xxg[i]; }
         pf.ig11 = (float)c->poly.ig11; pf.ig03 = (float)c->poly.ig03; pf.ig33 = (float)c->poly.ig33; pf.ig55 = (float)c->poly.ig55;
         const int TX = 128 - 2 * np;
-        dim3 g((L.w + TX - 1) / TX, (L.h + 31) / 32, nb);
+        // 16-row tiles (128-thread CTAs, 24 KB of shared memory, eight resident CTAs) overlap the load-latency phase of one
+        // CTA with the arithmetic of the others better than 32-row tiles: 422 vs 446 us per launch (RC_POLYEXP_ROWS=32: old form)
+        static const int rows = getenv("RC_POLYEXP_ROWS") ? atoi(getenv("RC_POLYEXP_ROWS")) : 16;
+#define RC_PX(NPV) \
+    do { if (rows == 16) polyexp_fast_kernel<NPV, 16><<<dim3((L.w + TX - 1) / TX, (L.h + 15) / 16, nb), 128, 0, c->stream>>>( \
+                 L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf); \
+         else polyexp_fast_kernel<NPV, 32><<<dim3((L.w + TX - 1) / TX, (L.h + 31) / 32, nb), 256, 0, c->stream>>>( \
+                 L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf); } while (0)
         switch (np) {
-        case 4: polyexp_fast_kernel<4><<<g, 256, 0, c->stream>>>(L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf); break;
-        case 6: polyexp_fast_kernel<6><<<g, 256, 0, c->stream>>>(L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf); break;
-        case 8: polyexp_fast_kernel<8><<<g, 256, 0, c->stream>>>(L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf); break;
-        case 12: polyexp_fast_kernel<12><<<g, 256, 0, c->stream>>>(L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf); break;
-        default: polyexp_fast_kernel<16><<<g, 256, 0, c->stream>>>(L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf); break;
+        case 4: RC_PX(4); break;
+        case 6: RC_PX(6); break;
+        case 8: RC_PX(8); break;
+        case 12: RC_PX(12); break;
+        default: RC_PX(16); break;
         }
+#undef RC_PX
         return;
     }
     constexpr int TX = 64, TY = 32;
