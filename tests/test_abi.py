@@ -66,3 +66,24 @@ def test_header_is_plain_c_and_cpp(tmp_path):
     inc = os.path.dirname(hdr)
     subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src_c)])
     subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src_cpp)])
+
+
+def test_new_entry_points_reject_null_context_without_cuda():
+    """The round-2 entry points (multi-GPU, sharded stream, mask format, averageVector) validate their arguments before any
+    CUDA call: a NULL context is RC_ERR_INVALID on a machine without a GPU."""
+    import ctypes as C
+    from ripcurrents_b200 import capi
+    lib = capi.load()
+    null = C.c_void_p(0)
+    buf = C.create_string_buffer(128)
+    assert lib.rc_comm_init(null, buf, 0, 1) == -1
+    assert lib.rc_comm_attach(null, null, 0, 1) == -1
+    assert lib.rc_comm_destroy(null) == -1
+    assert lib.rc_allreduce_accumulators(null, null, null, null) == -1
+    assert lib.rc_shard_configure(null, 10, 0) == -1
+    assert lib.rc_shard_step(null, null, C.c_size_t(0), C.c_size_t(0), 0, 0, null, null) == -1
+    assert lib.rc_shard_report(null, 0, null, null, null) == -1
+    assert lib.rc_shard_window_get(null, null) == -1
+    assert lib.rc_set_mask_format(null, 1) == -1
+    assert lib.rc_average_vector(null, null, null, C.c_size_t(0), 0, 0, null, null, 300, C.c_float(2.0), C.c_float(0.0)) == -1
+    assert lib.rc_comm_unique_id(None) == -1
