@@ -357,7 +357,8 @@ def measure_sharded_stream(torch, dist, dev, stream, rank, world, steps, frames)
     all-gathered for exact thresholds, the window mean is sharded by pixel band (all-to-all of flow bands), accumulators are
     all-reduced at the end.  Strong scaling: the stream is the same at every N, value = pairs of the stream per second."""
     from ripcurrents_b200 import Context, capi
-    BS = 32
+    BS = 32        # pairs per rank and super-block (63 was measured too: 9.29 k at one GPU but only 1.74x at two -- the larger
+                   # NCCL send/recv group shares the SMs with the flow kernels for longer; 32: 9.04 k and 1.92x)
     period = 2 * (CLIP_FRAMES - 1)
     order = (list(range(CLIP_FRAMES)) + list(range(CLIP_FRAMES - 2, 0, -1)))
     order = order + order[:BS + 2]
