@@ -552,7 +552,8 @@ struct PolyCoefF {
 };
 
 // TY = 32 rows per CTA (256 threads) or 16 (128 threads: half the shared memory, twice the resident CTAs; RC_POLYEXP_ROWS)
-template <int NP, int TY>
+// NC = taps per side that are evaluated (<= NP, the tile radius, which the 16-byte shared-memory windows need even)
+template <int NP, int TY, int NC = NP>
 __global__ void __launch_bounds__(TY * 8)
 polyexp_fast_kernel(const float* __restrict__ I, size_t istride, int w, int h, int pitch, float* __restrict__ R,
                     size_t plane, int first_slot, int nslots, PolyCoefF pc)
@@ -570,12 +571,12 @@ polyexp_fast_kernel(const float* __restrict__ I, size_t istride, int w, int h, i
         const int ybase = y0 + seg * VB - NP;
         float win[WIN];
 #pragma unroll
-        for (int j = 0; j < WIN; j++) win[j] = __ldg(I + (size_t)clampi(ybase + j, 0, h - 1) * pitch + gx);
+        for (int j = NP - NC; j < WIN - (NP - NC); j++) win[j] = __ldg(I + (size_t)clampi(ybase + j, 0, h - 1) * pitch + gx);
 #pragma unroll
         for (int i = 0; i < VB; i++) {
             float r0 = win[i + NP] * pc.g[0], r1 = 0.f, r2 = 0.f;
 #pragma unroll
-            for (int k = 1; k <= NP; k++) {
+            for (int k = 1; k <= NC; k++) {
                 float up = win[i + NP - k], dn = win[i + NP + k];
                 float p = up + dn;
                 r0 = fmaf(pc.g[k], p, r0);
@@ -603,7 +604,7 @@ polyexp_fast_kernel(const float* __restrict__ I, size_t istride, int w, int h, i
             for (int i = 0; i < 4; i++) {
                 float a1 = wv[NP + i] * pc.g[0], a2 = 0.f, a4 = 0.f;
 #pragma unroll
-                for (int k = 1; k <= NP; k++) {
+                for (int k = 1; k <= NC; k++) {
                     float p = wv[NP + i + k], m = wv[NP + i - k];
                     float tg = p + m;
                     a1 = fmaf(tg, pc.g[k], a1);
@@ -628,7 +629,7 @@ polyexp_fast_kernel(const float* __restrict__ I, size_t istride, int w, int h, i
             for (int i = 0; i < 4; i++) {
                 float a5 = wv[NP + i] * pc.g[0];
 #pragma unroll
-                for (int k = 1; k <= NP; k++) a5 = fmaf(wv[NP + i + k] + wv[NP + i - k], pc.g[k], a5);
+                for (int k = 1; k <= NC; k++) a5 = fmaf(wv[NP + i + k] + wv[NP + i - k], pc.g[k], a5);
                 o2[i] = fmaf(a5, pc.ig33, t1[i]);
             }
             // r1 window: b3 (g), b6 (xg, antisymmetric)
@@ -640,7 +641,7 @@ polyexp_fast_kernel(const float* __restrict__ I, size_t istride, int w, int h, i
             for (int i = 0; i < 4; i++) {
                 float a3 = wv[NP + i] * pc.g[0], a6 = 0.f;
 #pragma unroll
-                for (int k = 1; k <= NP; k++) {
+                for (int k = 1; k <= NC; k++) {
                     float p = wv[NP + i + k], m = wv[NP + i - k];
                     a3 = fmaf(p + m, pc.g[k], a3);
                     a6 = fmaf(p - m, pc.xg[k], a6);
@@ -1903,6 +1904,7 @@ static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
     const size_t istride = (size_t)L.pitch * L.h;
     KScope ks(c, K_POLYEXP, 24.0 * L.w * L.h * nb);
     int np = c->strict ? 0 : (c->poly.n_eff + 3) / 4 * 4;
+    const bool seven = !c->strict && c->poly.n_eff == 7;                      // tile radius 8, seven taps evaluated
     if (!c->strict && c->poly.n_eff > 4 && c->poly.n_eff <= 6) np = 6;      // taps per side: 4, 6, 8, 12 or 16
     if (np > 16) np = 0;
     static const bool packed = getenv("RC_POLYEXP") && !strcmp(getenv("RC_POLYEXP"), "packed");
@@ -1926,7 +1928,10 @@ static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
         if (encode && encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, L.I, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
             PolyCoefF pf;
-            for (int i = 0; i <= RC_MAX_POLY_N; i++) { pf.g[i] = c->poly.g[i]; pf.xg[i] = c->poly.xg[i]; pf.xxg[i] = c->poly.xxg[i]; }
+            for (int i = 0; i <= RC_MAX_POLY_N; i++) {      // taps beyond n_eff are dropped in every fast variant
+                const bool on = i <= c->poly.n_eff;
+                pf.g[i] = on ? c->poly.g[i] : 0.f; pf.xg[i] = on ? c->poly.xg[i] : 0.f; pf.xxg[i] = on ? c->poly.xxg[i] : 0.f;
+            }
             pf.ig11 = (float)c->poly.ig11; pf.ig03 = (float)c->poly.ig03; pf.ig33 = (float)c->poly.ig33; pf.ig55 = (float)c->poly.ig55;
             const int TX = 128 - 2 * 8;
             dim3 g((L.w + TX - 1) / TX, (L.h + 31) / 32, nb);
@@ -1938,8 +1943,9 @@ static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
     if (np && packed && np % 4 == 0) {
         PolyCoefF2 p2;
         for (int i = 0; i <= 16; i++) {
-            p2.g[i] = make_float2(c->poly.g[i], c->poly.g[i]); p2.xg[i] = make_float2(c->poly.xg[i], c->poly.xg[i]);
-            p2.xxg[i] = make_float2(c->poly.xxg[i], c->poly.xxg[i]);
+            const float g = i <= c->poly.n_eff ? c->poly.g[i] : 0.f, xg = i <= c->poly.n_eff ? c->poly.xg[i] : 0.f;
+            const float xxg = i <= c->poly.n_eff ? c->poly.xxg[i] : 0.f;
+            p2.g[i] = make_float2(g, g); p2.xg[i] = make_float2(xg, xg); p2.xxg[i] = make_float2(xxg, xxg);
         }
         p2.ig11 = (float)c->poly.ig11; p2.ig03 = (float)c->poly.ig03; p2.ig33 = (float)c->poly.ig33; p2.ig55 = (float)c->poly.ig55;
         const int TX = 128 - 2 * np;
@@ -1954,7 +1960,10 @@ static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
     }
     if (np) {
         PolyCoefF pf;
-        for (int i = 0; i <= RC_MAX_POLY_N; i++) { pf.g[i] = c->poly.g[i]; pf.xg[i] = c->poly.xg[i]; pf.xxg[i] = c->poly.xxg[i]; }
+        for (int i = 0; i <= RC_MAX_POLY_N; i++) {
+            const bool on = i <= c->poly.n_eff;
+            pf.g[i] = on ? c->poly.g[i] : 0.f; pf.xg[i] = on ? c->poly.xg[i] : 0.f; pf.xxg[i] = on ? c->poly.xxg[i] : 0.f;
+        }
         pf.ig11 = (float)c->poly.ig11; pf.ig03 = (float)c->poly.ig03; pf.ig33 = (float)c->poly.ig33; pf.ig55 = (float)c->poly.ig55;
         const int TX = 128 - 2 * np;
         // 16-row tiles (128-thread CTAs, 24 KB of shared memory, eight resident CTAs) overlap the load-latency phase of one
@@ -1965,6 +1974,11 @@ static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
                  L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf); \
          else polyexp_fast_kernel<NPV, 32><<<dim3((L.w + TX - 1) / TX, (L.h + 31) / 32, nb), 256, 0, c->stream>>>( \
                  L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf); } while (0)
+        if (seven && rows == 16) {
+            polyexp_fast_kernel<8, 16, 7><<<dim3((L.w + TX - 1) / TX, (L.h + 15) / 16, nb), 128, 0, c->stream>>>(
+                L.I, istride, L.w, L.h, L.pitch, L.R, L.plane, first_slot, nslots, pf);
+            return;
+        }
         switch (np) {
         case 4: RC_PX(4); break;
         case 6: RC_PX(6); break;
