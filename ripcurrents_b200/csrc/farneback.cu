@@ -546,6 +546,9 @@ __global__ void polyexp_strict_kernel(const float* __restrict__ I, size_t istrid
 //  phase H: thread = (row, 4 adjacent outputs): its (4 + 2*NP)-wide window of each vertical sum is read with
 //           conflict-free 16-byte shared loads; six symmetric/antisymmetric FMA chains; 16-byte plane stores.
 // ---------------------------------------------------------------------------------------------------
+#ifndef RC_POLY_SW
+#define RC_POLY_SW 144
+#endif
 struct PolyCoefF {
     float g[RC_MAX_POLY_N + 1], xg[RC_MAX_POLY_N + 1], xxg[RC_MAX_POLY_N + 1];
     float ig11, ig03, ig33, ig55;
@@ -558,7 +561,9 @@ __global__ void __launch_bounds__(TY * 8)
 polyexp_fast_kernel(const float* __restrict__ I, size_t istride, int w, int h, int pitch, float* __restrict__ R,
                     size_t plane, int first_slot, int nslots, PolyCoefF pc)
 {
-    constexpr int TX = 128 - 2 * NP, SW = 128, VB = 16, WIN = VB + 2 * NP, NTHR = TY * 8;
+    // 128 columns are used; with 16-row tiles the row pitch of 144 floats (the 32-row form is at the 48 KB static limit) shifts consecutive rows by 16 banks, so a quarter-warp of phase H
+    // whose eight 16-byte windows straddle two rows (28 groups per row) still touches 32 distinct banks
+    constexpr int TX = 128 - 2 * NP, SW = TY == 16 ? RC_POLY_SW : 128, VB = 16, WIN = VB + 2 * NP, NTHR = TY * 8;
     __shared__ __align__(16) float sr[3][TY][SW];
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const int tid = threadIdx.x;
