@@ -169,6 +169,32 @@ def test_window_rearm_and_clip_restart(oracle):
     c.close()
 
 
+@pytest.mark.parametrize("W,B,nframes", [(100, 12, 133), (1, 4, 14)])
+def test_window_of_100_frames_wraps(oracle, W, B, nframes):
+    """main.cpp:1505-1515: the W = 100 sliding window of the reference's second driver, through the batched pipeline, long
+    enough for the ring to wrap (132 pairs): the mean equals the sequential oracle on the GPU's own flows bit for bit at
+    every batch boundary.  W = 1 (the mean IS the latest flow, up to the rounding of avg - old + new) is the degenerate end."""
+    from ripcurrents_b200 import Context, synth
+    w, h = 96, 64
+    fr = np.stack(synth.clip(w, h, nframes, seed=15))
+    P = (0.5, 1, 3, 2, 5, 1.1, 0)
+    c = Context(0)
+    c.flow_configure_batch(w, h, *P, B); c.hist_reset(); c.window_configure(w, h, W)
+    c.process_frames(fr[:1], 0)
+    avg = np.zeros(h * w * 2, np.float32); ring = np.zeros((W, h * w * 2), np.float32)
+    pair = 0
+    for lo in range(1, len(fr), B):
+        nb = min(B, len(fr) - lo)
+        k, _ = c.process_frames(fr[lo:lo + nb], lo)
+        assert k == nb
+        for i in range(nb):
+            oracle.window_update(avg, ring[pair % W], c.flow_host_at(nb - 1 - i), W)
+            pair += 1
+        assert np.array_equal(c.window_get().ravel(), avg), lo
+    assert pair == nframes - 1
+    c.close()
+
+
 def test_sharded_super_blocks_on_gpu(oracle):
     """GpuBackend is re-entrant: a 13-pair clip in super-blocks of 2 'ranks' x 3 pairs (two contexts on this GPU, the
     all-gather / all-reduce done by hand) equals the sequential pipeline frame by frame."""
