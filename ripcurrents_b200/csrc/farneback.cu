@@ -53,25 +53,33 @@ __device__ __forceinline__ void resize_coef(int d, int src, double scale, int& s
 // resize to (dw, dh).  One kernel per layer: a CTA owns a TXD x TYD destination tile, stages the u8 source region
 // it depends on in shared memory (reflected at the image border), blurs horizontally only at the (up to) two source
 // columns each destination column samples, then vertically only at the two sampled rows, and combines.
+// The staged region stays u8 (converted tap by tap in the horizontal pass): interior tiles copy it with 4-byte cp.async
+// -- every word of the CTA in flight at once, no registers, no conversion pass -- and it is a quarter of the fp32 size, so
+// deep layers (scale 1/8, 1/16: 17- and 39-tap windows) get 4x larger destination tiles and a third less halo.
 // HBM traffic: the u8 frame once per layer (L2-resident after the first layer) + 4 B per destination pixel.
 // ---------------------------------------------------------------------------------------------------
 struct PyrArgs {
     const uint8_t* img; size_t step, fstride; int W, H;
     int dw, dh; double sxs, sys; int two;
     float* out; int pitch; size_t ostride;
-    int TXD, TYD, SRW, SRH;
+    int TXD, TYD, SRW, SRH, SRWB;      // SRWB: row pitch of the staged region in bytes (multiple of 4, odd word count)
 };
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
 
 __global__ void __launch_bounds__(256)
 pyr_tile_kernel(PyrArgs a, SmoothCoef sc)
 {
     extern __shared__ __align__(16) unsigned char psm[];
-    const int TXD = a.TXD, TYD = a.TYD, SRW = a.SRW, SRH = a.SRH;
+    const int TXD = a.TXD, TYD = a.TYD, SRW = a.SRW, SRH = a.SRH, SRWB = a.SRWB;
     const int SRHP = SRH | 1;                                          // odd pitch of the transposed H-blur buffer
     const int lx = 31 - __clz(TXD);                                    // TXD is a power of two
     float2* sT = reinterpret_cast<float2*>(psm);                       // [TXD][SRHP] horizontally blurred pairs
-    float* sS = reinterpret_cast<float*>(sT + (size_t)TXD * SRHP);     // [SRH][SRW] source region as fp32
-    int* cS = reinterpret_cast<int*>(sS + (size_t)SRH * SRW);          // [TXD] sx, [TYD] sy
+    uint8_t* sS = reinterpret_cast<uint8_t*>(sT + (size_t)TXD * SRHP); // [SRH][SRWB] source region, u8
+    int* cS = reinterpret_cast<int*>(sS + (size_t)SRH * SRWB);         // [TXD] sx, [TYD] sy
     float* cF = reinterpret_cast<float*>(cS + TXD + TYD);              // [TXD] fx, [TYD] fy
     int* gX = reinterpret_cast<int*>(cF + TXD + TYD);                  // [SRW] reflected source column of region col
     const int tid = threadIdx.x, r = sc.ksize / 2, ks = sc.ksize;
@@ -95,33 +103,38 @@ pyr_tile_kernel(PyrArgs a, SmoothCoef sc)
     const int ox = cS[0] - r, oy = cS[TXD] - r;
     for (int i = tid; i < SRW; i += 256) gX[i] = reflect101(ox + i, a.W);
     __syncthreads();
-    // stage the source region: warp = row.  Interior tiles of 4-byte aligned images read whole 32-bit words
-    // (coalesced, 4 pixels per load, several rows in flight); border / unaligned tiles gather bytes through the
-    // reflected column table.
-    const bool interior = ox >= 0 && ox + SRW <= a.W && oy >= 0 && oy + SRH <= a.H && (a.step & 3) == 0 &&
-                          (reinterpret_cast<size_t>(img) & 3) == 0;
-    if (interior) {
-        const int a0 = ox & ~3, sh = ox & 3;
-        const int nwords = (SRW + sh + 3) >> 2;
-#pragma unroll 4
+    // stage the source region: warp = row.  4-byte aligned images copy whole 32-bit words asynchronously (region column 0
+    // sits `sh` bytes into the row).  Tiles on the image border do the same for the part of every row that lies inside the
+    // image (rows outside it copy their REFLECT_101 mirror row) and then fill the few columns outside the image from their
+    // mirror columns, which are inside the staged region; unaligned images gather bytes through the reflected column table.
+    const bool aligned = (a.step & 3) == 0 && (reinterpret_cast<size_t>(img) & 3) == 0 && (a.W & 3) == 0;
+    const int sh = aligned ? (ox & 3) : 0;
+    if (aligned) {
+        const int a0 = ox & ~3;                                          // image column of the row's first word (may be < 0)
+        const int w_lo = a0 < 0 ? (-a0) >> 2 : 0;                        // first / one-past-last word inside the image
+        const int w_hi = min((SRW + sh + 3) >> 2, (a.W - a0) >> 2);
         for (int ry = wrp; ry < SRH; ry += 8) {
-            const unsigned int* grow = reinterpret_cast<const unsigned int*>(img + (size_t)(oy + ry) * a.step + a0);
-            float* srow = sS + ry * SRW - sh;
-            for (int j = lane; j < nwords; j += 32) {
-                const unsigned int v = __ldg(grow + j);
-                const int c = 4 * j;
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int col = c + b - sh;
-                    if (col >= 0 && col < SRW) srow[c + b] = (float)((v >> (8 * b)) & 0xffu);
+            const unsigned int* grow = reinterpret_cast<const unsigned int*>(img + (size_t)reflect101(oy + ry, a.H) * a.step) + (a0 >> 2);
+            unsigned int* srow = reinterpret_cast<unsigned int*>(sS + ry * SRWB);
+            for (int j = w_lo + lane; j < w_hi; j += 32) cp_async4(srow + j, grow + j);
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        if (ox < 0 || ox + SRW > a.W) {
+            __syncthreads();
+            const int nl = ox < 0 ? -ox : 0, nr = ox + SRW > a.W ? ox + SRW - a.W : 0;      // columns outside, left / right
+            for (int ry = wrp; ry < SRH; ry += 8) {
+                uint8_t* srow = sS + ry * SRWB + sh;
+                for (int i = lane; i < nl + nr; i += 32) {
+                    const int cidx = i < nl ? i : SRW - nr + (i - nl);
+                    srow[cidx] = srow[gX[cidx] - ox];
                 }
             }
         }
     } else {
         for (int ry = wrp; ry < SRH; ry += 8) {
             const uint8_t* grow = img + (size_t)reflect101(oy + ry, a.H) * a.step;
-            float* srow = sS + ry * SRW;
-            for (int rx = lane; rx < SRW; rx += 32) srow[rx] = (float)grow[gX[rx]];
+            uint8_t* srow = sS + ry * SRWB;
+            for (int rx = lane; rx < SRW; rx += 32) srow[rx] = grow[gX[rx]];
         }
     }
     __syncthreads();
@@ -133,18 +146,17 @@ pyr_tile_kernel(PyrArgs a, SmoothCoef sc)
         const int d1 = a.two ? (sx + 1 < a.W ? sx + 1 : a.W - 1) - sx : 0;
         const int c0 = sx - r - ox;
         for (int ry = lane; ry < SRH; ry += 32) {
-            const float* row = sS + ry * SRW + c0;
-            float prev = row[0];
-            float s0 = __fmul_rn(sc.k[0], prev), s1 = 0.f;
+            const uint8_t* row = sS + ry * SRWB + sh + c0;
+            float s0 = __fmul_rn(sc.k[0], (float)row[0]), s1 = 0.f;
             if (d1 == 1) {
                 for (int i = 1; i < ks; i++) {
-                    const float cur = row[i];
+                    const float cur = (float)row[i];
                     s0 = __fadd_rn(s0, __fmul_rn(sc.k[i], cur));
                     s1 = i == 1 ? __fmul_rn(sc.k[0], cur) : __fadd_rn(s1, __fmul_rn(sc.k[i - 1], cur));
                 }
-                s1 = __fadd_rn(s1, __fmul_rn(sc.k[ks - 1], row[ks]));
+                s1 = __fadd_rn(s1, __fmul_rn(sc.k[ks - 1], (float)row[ks]));
             } else {
-                for (int i = 1; i < ks; i++) s0 = __fadd_rn(s0, __fmul_rn(sc.k[i], row[i]));
+                for (int i = 1; i < ks; i++) s0 = __fadd_rn(s0, __fmul_rn(sc.k[i], (float)row[i]));
                 s1 = s0;        // identity resize, or the clamped last column (d1 == 0): both samples coincide
             }
             sT[tx * SRHP + ry] = make_float2(s0, s1);
@@ -2093,10 +2105,12 @@ void rc_launch_expand(rc_ctx* c, const uint8_t* d_frames, size_t step, size_t fs
         for (int i = 0; i < 6; i++) {
             a.TXD = cand[i][0]; a.TYD = cand[i][1];
             a.SRW = (int)(a.sxs * (a.TXD - 1)) + 2 * r + 4; a.SRH = (int)(a.sys * (a.TYD - 1)) + 2 * r + 4;
-            a.SRW |= 1;       // odd row pitch: column-strided reads of the staged region spread over the banks
-            smem = sizeof(float2) * (size_t)(a.SRH | 1) * a.TXD + 4 * (size_t)a.SRH * a.SRW + 8 * (size_t)(a.TXD + a.TYD) +
+            // u8 rows, up to 3 bytes of alignment shift, an odd number of 32-bit words per row: the row-strided byte reads
+            // of the horizontal pass (lane = staged row) spread over the banks
+            a.SRWB = 4 * (((a.SRW + 3 + 3) >> 2) | 1);
+            smem = sizeof(float2) * (size_t)(a.SRH | 1) * a.TXD + (size_t)a.SRH * a.SRWB + 8 * (size_t)(a.TXD + a.TYD) +
                    4 * (size_t)a.SRW;
-            if (smem <= 100 * 1024) break;
+            if (smem <= 72 * 1024) break;        // three or more resident CTAs
         }
         {
             dim3 g((L.w + a.TXD - 1) / a.TXD, (L.h + a.TYD - 1) / a.TYD, nb);
