@@ -16,6 +16,7 @@
 // (CV_32FC2, the output format).  Every array has a leading batch dimension: one
 // launch processes all frame pairs of a batch (blockIdx.z), which is what fills 148 SMs on the small pyramid layers.
 #include <string.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include "rc_internal.h"
 #include <cuda.h>
@@ -1488,14 +1489,25 @@ flow_layer_kernel(FlowArgs a)
 // updateMatrices launch and its 20 B/px write + 20 B/px read.
 // NTHR = 256 (16 rows per step) or 128 (8 rows per step: half the shared memory per CTA, twice the resident CTAs -- more
 // independent phase machines per SM to cover each other's updateMatrices gathers and barriers; RC_MARCH_THREADS)
+// Staging of M rows (iterations after the first): interior steps -- every staged column and row inside the image -- are ONE
+// cp.async.bulk.tensor.3d (TMA) per step, issued by one thread behind an mbarrier: box = WPA columns x RB rows x 5 planes of
+// the layer's M tensor [pair][buffer][plane][row][column].  Steps that touch the image border (replicate clamping, which the
+// copy engine's zero fill cannot express) and contexts without a tensor map use per-element cp.async.  ncu before this:
+// a fifth of the final iteration's instructions (and 78 % of its issue slots were busy) were staging address arithmetic.
 template <int M, bool FUSE, bool BOX, bool FIRST, int NTHR>
 __global__ void __launch_bounds__(NTHR, NTHR == 256 ? (FUSE ? 3 : 2) : (FUSE ? 6 : 4))
-flow_march_kernel(FlowArgs a, int mi, int SEG)
+flow_march_kernel(FlowArgs a, int mi, int SEG, const __grid_constant__ CUtensorMap tmM, int use_tma)
 {
-    constexpr int TX = 64, RB = NTHR / 16, NWARP = NTHR / 32, WP = TX + 2 * M, WPA = (WP + 3) & ~3, RING = RB + 2 * M;
-    extern __shared__ __align__(16) float msm[];
-    float* sRaw = msm;                         // [RB][5][WPA]
+    // D: the staged rows start at column x0 - M - D, the first 16-byte aligned column at or before x0 - M (the TMA copy
+    // needs that alignment; the per-element path then copies two floats per cp.async); the blurs read from column D on
+    constexpr int TX = 64, RB = NTHR / 16, NWARP = NTHR / 32, D = ((M + 3) & ~3) - M, WP = TX + 2 * M, WPA = (WP + D + 3) & ~3,
+                  RING = RB + 2 * M;
+    extern __shared__ __align__(16) float msm_raw[];
+    // the TMA destination must be 128-byte aligned; static shared memory precedes the dynamic part, so align by hand
+    float* msm = msm_raw + ((128u - (smem_u32(msm_raw) & 127u)) & 127u) / 4;
+    float* sRaw = msm;                         // [5][RB][WPA]
     float* sRing = msm + RB * 5 * WPA;         // [RING][5][TX]
+    __shared__ __align__(8) unsigned long long tbar;
     __shared__ unsigned int sH[FUSE ? 1 : RC_HIST_CELLS];
     __shared__ unsigned short sKeys[FUSE ? 1 : 256];
     __shared__ int sNKeys;
@@ -1517,7 +1529,18 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
     int ns = 0, no = 0;
     // stage: warp per (row, channel); asynchronous copies (global -> shared without registers), so the rows of step b+1
     // are in flight while step b is blurred vertically and solved
-    const bool interior_x = x0 - M >= 0 && x0 - M + WP <= w;
+    const bool interior_x = x0 - M - D >= 0 && x0 - M + WP + 1 <= w;
+    const bool tma_x = !FIRST && use_tma && interior_x;
+    const unsigned long long tm_addr = reinterpret_cast<unsigned long long>(&tmM);     // param space (__grid_constant__)
+    bool staged_tma = false;
+    unsigned tphase = 0;
+    if (!FIRST && use_tma) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     const float2* coarse = FIRST && a.coarse ? reinterpret_cast<const float2*>(a.coarse + (size_t)j * a.coarse_stride) : nullptr;
     auto stage = [&](int first, int cnt) {
         if constexpr (FIRST) {
@@ -1542,26 +1565,38 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
                         float mm[5];
                         update_matrices_core<false>(xs[q], y, fi.x, fi.y, w, h, R0, R1, a.pitch, mm);
 #pragma unroll
-                        for (int c = 0; c < 5; c++) sRaw[(r * 5 + c) * WPA + rx] = mm[c];
+                        for (int c = 0; c < 5; c++) sRaw[(c * RB + r) * WPA + D + rx] = mm[c];
                     }
                 }
             }
         } else {
+            const int ytop = y0 - M + first;
+            staged_tma = tma_x && ytop >= 0 && ytop + cnt <= h;                // CTA-uniform
+            if (staged_tma) {
+                if (tid == 0) {
+                    constexpr unsigned BYTES = 5 * RB * WPA * sizeof(float);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tbar)), "r"(BYTES) : "memory");
+                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                                 ::"r"(smem_u32(sRaw)), "l"(tm_addr), "r"(x0 - M - D), "r"(ytop), "r"((j * 2 + mi) * 5), "r"(smem_u32(&tbar))
+                                 : "memory");
+                }
+                return;
+            }
             for (int rc = wrp; rc < cnt * 5; rc += NWARP) {
                 const int r = rc / 5, c = rc - 5 * r;
                 const float* grow = Min + (size_t)c * a.plane + (size_t)clampi(y0 - M + first + r, 0, h - 1) * a.pitch;
-                float* dst = sRaw + (r * 5 + c) * WPA;
-                if (M % 2 == 0 && interior_x) {            // no column clamping, 8-byte aligned: half the copies
+                float* dst = sRaw + (c * RB + r) * WPA;
+                if (interior_x) {                          // no column clamping, 8-byte aligned: half the copies
 #pragma unroll
-                    for (int q = 0; q < (WP / 2 + 31) / 32; q++) {
+                    for (int q = 0; q < ((WP + D + 1) / 2 + 31) / 32; q++) {
                         const int rx = lane + 32 * q;
-                        if (rx < WP / 2) __pipeline_memcpy_async(dst + 2 * rx, grow + (x0 - M) + 2 * rx, 8);
+                        if (rx < (WP + D + 1) / 2) __pipeline_memcpy_async(dst + 2 * rx, grow + (x0 - M - D) + 2 * rx, 8);
                     }
                 } else {
 #pragma unroll
                     for (int q = 0; q < (WP + 31) / 32; q++) {
                         const int rx = lane + 32 * q;
-                        if (rx < WP) __pipeline_memcpy_async(dst + rx, grow + clampi(x0 - M + rx, 0, w - 1), 4);
+                        if (rx < WP) __pipeline_memcpy_async(dst + D + rx, grow + clampi(x0 - M + rx, 0, w - 1), 4);
                     }
                 }
             }
@@ -1571,16 +1606,25 @@ flow_march_kernel(FlowArgs a, int mi, int SEG)
     if (!FIRST) stage(0, min(RB, total));
     while (ns < total) {
         const int cnt = min(RB, total - ns);
-        if (FIRST) stage(ns, cnt); else __pipeline_wait_prior(0);
+        if (FIRST) stage(ns, cnt);
+        else if (staged_tma) {
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(smem_u32(&tbar)), "r"(tphase) : "memory");
+            tphase ^= 1;
+        } else __pipeline_wait_prior(0);
         __syncthreads();
-        // ---- horizontal blur: item = (row, channel, group of 4 pixels)
-        for (int it = tid; it < cnt * 5 * (TX / 4); it += NTHR) {
+        // ---- horizontal blur: item = (channel, row, group of 4 pixels); staged row rc = c * RB + r
+        for (int it = tid; it < 5 * RB * (TX / 4); it += NTHR) {
             const int xg = it & 15, rc = it >> 4;
-            const int r = rc / 5, c = rc - 5 * r;
-            float win[4 + 2 * M + 3];
+            const int c = rc / RB, r = rc - c * RB;
+            if (r >= cnt) continue;
+            float wbuf[(4 + 2 * M + D + 3) / 4 * 4];
 #pragma unroll
-            for (int q = 0; q < (4 + 2 * M + 3) / 4; q++)
-                *reinterpret_cast<float4*>(win + 4 * q) = *reinterpret_cast<const float4*>(sRaw + rc * WPA + 4 * xg + 4 * q);
+            for (int q = 0; q < (4 + 2 * M + D + 3) / 4; q++)
+                *reinterpret_cast<float4*>(wbuf + 4 * q) = *reinterpret_cast<const float4*>(sRaw + rc * WPA + 4 * xg + 4 * q);
+            const float* win = wbuf + D;
             float o[4];
             if (BOX) {
                 float run = win[0];
@@ -1901,7 +1945,7 @@ void rc_farneback_init_device(int device)
         const int tiled_max = (int)(sizeof(float) * ((size_t)(16 + 32) * (64 + 32) + 16 * (size_t)(64 + 32)));
         cudaFuncSetAttribute(flow_iter_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled_max);
         cudaFuncSetAttribute(flow_iter_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled_max);
-        const int big = (int)(sizeof(float) * (16 * 5 * 84 + 36 * 5 * 64));
+        const int big = (int)(128 + sizeof(float) * (16 * 5 * 88 + 36 * 5 * 64));
 #define RC_CFG1(MM, FU, BX) \
     cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
     cudaFuncSetAttribute(flow_march_kernel<MM, FU, BX, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
@@ -1913,6 +1957,21 @@ void rc_farneback_init_device(int device)
 #undef RC_CFG1
         cudaGetLastError();
     });
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point, so that the library keeps linking cudart only
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder()
+{
+    static TensorMapEncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess) fn = nullptr;
+        return reinterpret_cast<TensorMapEncodeFn>(fn);
+    }();
+    return encode;
 }
 
 static void launch_polyexp(rc_ctx* c, Layer& L, int nb, int first_slot)
@@ -2224,12 +2283,29 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         if ((long long)nb * ((L.w + 63) / 64) * mnseg < 148LL * 3 * 8) mnseg = (L.h + 127) / 128;
         const int MSEG = march_seg_env > 0 ? march_seg_env : ((L.h + mnseg - 1) / mnseg + 3) & ~3;
         dim3 gm(nb, (L.w + 63) / 64, (L.h + MSEG - 1) / MSEG);
-        const size_t msm = sizeof(float) * (16 * 5 * (size_t)((64 + 2 * m + 3) & ~3) + (size_t)(16 + 2 * m) * 5 * 64);
-        const size_t msm128 = sizeof(float) * (8 * 5 * (size_t)((64 + 2 * m + 3) & ~3) + (size_t)(8 + 2 * m) * 5 * 64);
+        const size_t msm = 128 + sizeof(float) * (16 * 5 * (size_t)((64 + 2 * m + (((m + 3) & ~3) - m) + 3) & ~3) + (size_t)(16 + 2 * m) * 5 * 64);
+        const size_t msm128 = 128 + sizeof(float) * (8 * 5 * (size_t)((64 + 2 * m + (((m + 3) & ~3) - m) + 3) & ~3) + (size_t)(8 + 2 * m) * 5 * 64);
         // 128-thread CTAs (8 rows per step, 35 KB of shared memory, six resident CTAs) for half-widths up to 5: +2.5 % on
         // Gaussian winsize 10; at half-width 10 the ring alone is 36 KB, only four such CTAs fit and the 256-thread form wins
         static const int march_threads_env = getenv("RC_MARCH_THREADS") ? atoi(getenv("RC_MARCH_THREADS")) : 0;
         const int march_threads = march_threads_env ? march_threads_env : (m <= 5 ? 128 : 256);
+        // tensor map of this layer's M buffers seen as [B * 2 * 5 planes][h][pitch] (zero fill outside the image: such steps
+        // do not use it); box = staged columns x rows per step x 5 planes.  RC_MARCH_TMA=0 keeps the per-element copies.
+        CUtensorMap tmM;
+        memset(&tmM, 0, sizeof tmM);
+        int use_tma = 0;
+        static const bool tma_off = getenv("RC_MARCH_TMA") && atoi(getenv("RC_MARCH_TMA")) == 0;
+        if (march && T > 1 && !tma_off) {
+            const int rb = march_threads / 16, wpa = (64 + 2 * m + (((m + 3) & ~3) - m) + 3) & ~3;
+            const cuuint64_t gdim[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)10 * c->B};
+            const cuuint64_t gstr[2] = {(cuuint64_t)L.pitch * 4, (cuuint64_t)L.plane * 4};
+            const cuuint32_t bx[3] = {(cuuint32_t)wpa, (cuuint32_t)rb, 5}, es[3] = {1, 1, 1};
+            TensorMapEncodeFn enc = tensor_map_encoder();
+            if (enc && enc(&tmM, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, L.M, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                use_tma = 1;
+            if (getenv("RC_MARCH_TMA_DEBUG")) fprintf(stderr, "march tma: layer %dx%d pitch %d m %d rb %d wpa %d B %d -> %d\n", L.w, L.h, L.pitch, m, rb, wpa, c->B, use_tma);
+        }
         bool hist_fused = false;
         int mi = 0;
         for (int it = 0; it < T; it++) {
@@ -2239,10 +2315,10 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
                 if (spec) {
 #define RC_LAUNCH_MT(MM, FU, NT, SM) \
     do { if (it == 0) { \
-             if (box) flow_march_kernel<MM, FU, true, true, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG); \
-             else flow_march_kernel<MM, FU, false, true, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG); \
-         } else if (box) flow_march_kernel<MM, FU, true, false, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG); \
-         else flow_march_kernel<MM, FU, false, false, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG); } while (0)
+             if (box) flow_march_kernel<MM, FU, true, true, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG, tmM, 0); \
+             else flow_march_kernel<MM, FU, false, true, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG, tmM, 0); \
+         } else if (box) flow_march_kernel<MM, FU, true, false, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG, tmM, use_tma); \
+         else flow_march_kernel<MM, FU, false, false, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG, tmM, use_tma); } while (0)
 #define RC_LAUNCH_M(MM, FU) \
     do { if (march_threads == 128) RC_LAUNCH_MT(MM, FU, 128, msm128); else RC_LAUNCH_MT(MM, FU, 256, msm); } while (0)
                     if (m == 2) RC_LAUNCH_M(2, true); else if (m == 5) RC_LAUNCH_M(5, true); else RC_LAUNCH_M(10, true);
