@@ -1522,7 +1522,8 @@ flow_march_kernel(FlowArgs a, int mi, int SEG, const __grid_constant__ CUtensorM
     float kk[M + 1];
 #pragma unroll
     for (int i = 0; i <= M; i++) kk[i] = a.win.k[i];
-    const float ps = a.win.post_scale;
+    // window sums stay unscaled: the solve only needs the regulariser rescaled (solve_fast_unscaled)
+    const float eps_unscaled = 1e-3f / (a.win.post_scale * a.win.post_scale);
     const RView R0 = rview(a.R0(j), a.plane), R1 = rview(a.R1(j), a.plane);
     const int nout = min(SEG, h - y0), total = nout + 2 * M;          // staged row s <-> image row y0 - M + s (clamped)
     const int col = tid & 63, rbk = tid >> 6;                          // v-blur role
@@ -1666,16 +1667,16 @@ flow_march_kernel(FlowArgs a, int mi, int SEG, const __grid_constant__ CUtensorM
                     float run = win[0];
 #pragma unroll
                     for (int i = 1; i <= 2 * M; i++) run += win[i];
-                    s[0][c] = run * ps;
+                    s[0][c] = run;
 #pragma unroll
-                    for (int i = 1; i < 4; i++) { run += win[i + 2 * M] - win[i - 1]; s[i][c] = run * ps; }
+                    for (int i = 1; i < 4; i++) { run += win[i + 2 * M] - win[i - 1]; s[i][c] = run; }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         float v = win[i + M] * kk[0];
 #pragma unroll
                         for (int k = 1; k <= M; k++) v = fmaf(win[i + M + k] + win[i + M - k], kk[k], v);
-                        s[i][c] = v * ps;
+                        s[i][c] = v;
                     }
                 }
             }
@@ -1685,7 +1686,7 @@ flow_march_kernel(FlowArgs a, int mi, int SEG, const __grid_constant__ CUtensorM
                 const int y = y0 + o0 + i;
                 const bool in = x < w && o0 + i < lim;
                 float2 f = make_float2(0.f, 0.f);
-                if (in) f = solve_fast(s[i][0], s[i][1], s[i][2], s[i][3], s[i][4]);
+                if (in) f = solve_fast_unscaled(s[i][0], s[i][1], s[i][2], s[i][3], s[i][4], eps_unscaled);
                 if (FUSE) {
                     if (in) {
                         float mm[5];
