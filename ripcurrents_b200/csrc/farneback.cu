@@ -2266,7 +2266,12 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         const bool tiled = !c->strict && c->win.m >= 1 && c->win.m <= 16;
         const int m = c->win.m;
         const bool march = tiled && (m == 2 || m == 5 || m == 10);
-        if (!march) {      // the marching kernel computes M inside its first iteration
+        // RC_MARCH_FIRST=0 / =10: M of the first iteration from the stand-alone updateMatrices kernel (no halo recomputation,
+        // 20 B/px written and read back through the TMA staging) instead of inside the first marching launch -- for every
+        // half-width / only for half-width 10
+        static const int first_mode = getenv("RC_MARCH_FIRST") ? atoi(getenv("RC_MARCH_FIRST")) : 1;
+        const bool first_fused = march && !(first_mode == 0 || (first_mode == 10 && m == 10));
+        if (!first_fused) {      // otherwise the marching kernel computes M inside its first iteration
             KScope ks(c, K_UPDATE_MATRICES, (a.coarse ? 62.0 : 60.0) * npx);
             if (c->strict) update_matrices_kernel<true><<<g, b, 0, c->stream>>>(a, 0);
             else update_matrices_kernel<false><<<g, b, 0, c->stream>>>(a, 0);
@@ -2310,12 +2315,12 @@ void rc_launch_flows(rc_ctx* c, int nb, int prev_slot, float* const* flow_dst_ho
         bool hist_fused = false;
         int mi = 0;
         for (int it = 0; it < T; it++) {
-            const double first_extra = spec && it == 0 ? (a.coarse ? 22.0 : 20.0) : 0.0;   // R0 + R1 (+ coarse flow) instead of M
+            const double first_extra = first_fused && it == 0 ? (a.coarse ? 22.0 : 20.0) : 0.0;   // R0 + R1 (+ coarse flow) instead of M
             if (it < T - 1) {
                 KScope ks(c, K_FLOW_ITER_FUSED, (80.0 + first_extra) * npx);
                 if (spec) {
 #define RC_LAUNCH_MT(MM, FU, NT, SM) \
-    do { if (it == 0) { \
+    do { if (it == 0 && first_fused) { \
              if (box) flow_march_kernel<MM, FU, true, true, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG, tmM, 0); \
              else flow_march_kernel<MM, FU, false, true, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG, tmM, 0); \
          } else if (box) flow_march_kernel<MM, FU, true, false, NT><<<gm, NT, SM, c->stream>>>(a, mi, MSEG, tmM, use_tma); \
