@@ -51,3 +51,24 @@ def test_alternative_kernels_give_identical_bits(tmp_path, var, val):
     assert sorted(outs[0].files) == sorted(outs[1].files) and len(outs[0].files) == 5
     for k in outs[0].files:
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_march_tma_staging_gives_identical_bits(tmp_path):
+    """The marching kernel (winsize > 3) stages M with one TMA tensor copy per interior step; RC_MARCH_TMA=0 selects the
+    per-element cp.async copies everywhere.  Same data in the same shared-memory layout, so every flow must agree bit for bit
+    (six configurations: half-widths 2 / 5 / 10, box and Gaussian, ragged sizes, layers narrower than the TMA box)."""
+    import numpy as np
+    outs = []
+    for mode in ("default", "alt"):
+        env = dict(os.environ)
+        if mode == "alt":
+            env["RC_MARCH_TMA"] = "0"
+        path = str(tmp_path / (mode + ".npz"))
+        out = subprocess.run([sys.executable, os.path.join(HERE, "march_dump.py"), path], env=env, capture_output=True, text=True,
+                             timeout=600)
+        assert out.returncode == 0 and "dumped" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+        outs.append(np.load(path))
+    assert sorted(outs[0].files) == sorted(outs[1].files) and len(outs[0].files) == 6
+    for k in outs[0].files:
+        assert np.isfinite(outs[0][k]).all() and np.abs(outs[0][k]).max() > 0.1, k
+        assert np.array_equal(outs[0][k], outs[1][k]), k
