@@ -398,16 +398,17 @@ pyr3_kernel(Pyr3Args a)
             sHq[it] = make_float2(s0, s1);
         }
     }
-    // ---- layer 0: 4 adjacent pixels per item
+    // ---- layer 0: item = 4 adjacent pixels x 4 rows: the six horizontally blurred rows it needs are formed once (a 4 x 1
+    // item recomputes three per output row); per-pixel arithmetic and order unchanged
     {
         const float k0 = a.k3a[0], k1 = a.k3a[1], k2 = a.k3a[2];
         float* out = a.out[0] + (size_t)blockIdx.z * a.ostride[0];
-        for (int it = tid; it < TH * (TW / 4); it += 256) {
-            const int y = it >> 5, x4 = (it & 31) * 4;
+        for (int it = tid; it < (TH / 4) * (TW / 4); it += 256) {
+            const int y = (it >> 5) * 4, x4 = (it & 31) * 4;
             if (X0 + x4 >= W || Y0 + y >= H) continue;
-            float hb[3][4];
+            float hb[6][4];
 #pragma unroll
-            for (int rr = 0; rr < 3; rr++) {
+            for (int rr = 0; rr < 6; rr++) {
                 float w12[12];
                 lds12(sS + (y + 2 + rr) * SP + x4, w12);
                 const float* v = w12 + 3;                            // image row Y0 + y - 1 + rr, column X0 + x4 - 1
@@ -415,26 +416,31 @@ pyr3_kernel(Pyr3Args a)
                 for (int i = 0; i < 4; i++)
                     hb[rr][i] = __fadd_rn(__fadd_rn(__fmul_rn(k0, v[i]), __fmul_rn(k1, v[i + 1])), __fmul_rn(k2, v[i + 2]));
             }
-            float4 o;
-            o.x = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[0][0]), __fmul_rn(k1, hb[1][0])), __fmul_rn(k2, hb[2][0]));
-            o.y = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[0][1]), __fmul_rn(k1, hb[1][1])), __fmul_rn(k2, hb[2][1]));
-            o.z = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[0][2]), __fmul_rn(k1, hb[1][2])), __fmul_rn(k2, hb[2][2]));
-            o.w = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[0][3]), __fmul_rn(k1, hb[1][3])), __fmul_rn(k2, hb[2][3]));
-            *reinterpret_cast<float4*>(out + (size_t)(Y0 + y) * a.pitch[0] + X0 + x4) = o;
+#pragma unroll
+            for (int oy = 0; oy < 4; oy++) {
+                if (Y0 + y + oy >= H) break;
+                float4 o;
+                o.x = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[oy][0]), __fmul_rn(k1, hb[oy + 1][0])), __fmul_rn(k2, hb[oy + 2][0]));
+                o.y = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[oy][1]), __fmul_rn(k1, hb[oy + 1][1])), __fmul_rn(k2, hb[oy + 2][1]));
+                o.z = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[oy][2]), __fmul_rn(k1, hb[oy + 1][2])), __fmul_rn(k2, hb[oy + 2][2]));
+                o.w = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[oy][3]), __fmul_rn(k1, hb[oy + 1][3])), __fmul_rn(k2, hb[oy + 2][3]));
+                *reinterpret_cast<float4*>(out + (size_t)(Y0 + y + oy) * a.pitch[0] + X0 + x4) = o;
+            }
         }
     }
-    // ---- layer 1: 2 adjacent pixels per item (source window 4 rows x 6 columns)
+    // ---- layer 1: item = 2 adjacent pixels x 2 rows (source window 6 rows x 6 columns; the two rows share two of their
+    // four horizontally blurred source rows)
     {
         const float k0 = a.k3b[0], k1 = a.k3b[1], k2 = a.k3b[2];
         float* out = a.out[1] + (size_t)blockIdx.z * a.ostride[1];
         const int dw = W / 2, dh = H / 2;
-        for (int it = tid; it < (TH / 2) * (TW / 4); it += 256) {
-            const int y = it >> 5, x2 = (it & 31) * 2;                // layer-1 pixel (X0/2 + x2, Y0/2 + y)
+        for (int it = tid; it < (TH / 4) * (TW / 4); it += 256) {
+            const int y = (it >> 5) * 2, x2 = (it & 31) * 2;          // layer-1 pixels (X0/2 + x2 + {0,1}, Y0/2 + y + {0,1})
             const int X = X0 / 2 + x2, Y = Y0 / 2 + y;
             if (X >= dw || Y >= dh) continue;
-            float hb[4][4];
+            float hb[6][4];
 #pragma unroll
-            for (int rr = 0; rr < 4; rr++) {
+            for (int rr = 0; rr < 6; rr++) {
                 float w12[12];
                 lds12(sS + (2 * y + 2 + rr) * SP + 2 * x2, w12);
                 const float* v = w12 + 3;                            // image row 2Y - 1 + rr, column 2X - 1
@@ -442,22 +448,26 @@ pyr3_kernel(Pyr3Args a)
                 for (int i = 0; i < 4; i++)
                     hb[rr][i] = __fadd_rn(__fadd_rn(__fmul_rn(k0, v[i]), __fmul_rn(k1, v[i + 1])), __fmul_rn(k2, v[i + 2]));
             }
-            float r[2];
 #pragma unroll
-            for (int d = 0; d < 2; d++) {
-                float b[2][2];
+            for (int oy = 0; oy < 2; oy++) {
+                if (Y + oy >= dh) break;
+                float r[2];
 #pragma unroll
-                for (int sr = 0; sr < 2; sr++)
+                for (int d = 0; d < 2; d++) {
+                    float b[2][2];
 #pragma unroll
-                    for (int sc = 0; sc < 2; sc++) {
-                        const int c = 2 * d + sc;
-                        b[sr][sc] = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[sr][c]), __fmul_rn(k1, hb[sr + 1][c])), __fmul_rn(k2, hb[sr + 2][c]));
-                    }
-                const float top = __fadd_rn(__fmul_rn(b[0][0], 0.5f), __fmul_rn(b[0][1], 0.5f));
-                const float bot = __fadd_rn(__fmul_rn(b[1][0], 0.5f), __fmul_rn(b[1][1], 0.5f));
-                r[d] = __fadd_rn(__fmul_rn(top, 0.5f), __fmul_rn(bot, 0.5f));
+                    for (int sr = 0; sr < 2; sr++)
+#pragma unroll
+                        for (int sc = 0; sc < 2; sc++) {
+                            const int c = 2 * d + sc, r0 = 2 * oy + sr;
+                            b[sr][sc] = __fadd_rn(__fadd_rn(__fmul_rn(k0, hb[r0][c]), __fmul_rn(k1, hb[r0 + 1][c])), __fmul_rn(k2, hb[r0 + 2][c]));
+                        }
+                    const float top = __fadd_rn(__fmul_rn(b[0][0], 0.5f), __fmul_rn(b[0][1], 0.5f));
+                    const float bot = __fadd_rn(__fmul_rn(b[1][0], 0.5f), __fmul_rn(b[1][1], 0.5f));
+                    r[d] = __fadd_rn(__fmul_rn(top, 0.5f), __fmul_rn(bot, 0.5f));
+                }
+                *reinterpret_cast<float2*>(out + (size_t)(Y + oy) * a.pitch[1] + X) = make_float2(r[0], r[1]);
             }
-            *reinterpret_cast<float2*>(out + (size_t)Y * a.pitch[1] + X) = make_float2(r[0], r[1]);
         }
     }
     __syncthreads();
