@@ -1518,6 +1518,8 @@ flow_march_kernel(FlowArgs a, int mi, int SEG, const __grid_constant__ CUtensorM
     float* sRaw = msm;                         // [5][RB][WPA]
     float* sRing = msm + RB * 5 * WPA;         // [RING][5][TX]
     __shared__ __align__(8) unsigned long long tbar;
+    __shared__ int sColX[FIRST ? WP : 1], sColS[FIRST ? WP : 1];       // first iteration: clamped column, coarse column,
+    __shared__ float sColF[FIRST ? WP : 1];                            // coarse interpolation weight of every staged column
     __shared__ unsigned int sH[FUSE ? 1 : RC_HIST_CELLS];
     __shared__ unsigned short sKeys[FUSE ? 1 : 256];
     __shared__ int sNKeys;
@@ -1553,32 +1555,33 @@ flow_march_kernel(FlowArgs a, int mi, int SEG, const __grid_constant__ CUtensorM
         __syncthreads();
     }
     const float2* coarse = FIRST && a.coarse ? reinterpret_cast<const float2*>(a.coarse + (size_t)j * a.coarse_stride) : nullptr;
+    if (FIRST) {
+        for (int i = tid; i < WP; i += NTHR) {
+            const int xc = clampi(x0 - M + i, 0, w - 1);
+            int cs = 0; float cf = 0.f;
+            if (coarse) resize_coef(xc, a.cw, a.sxs, cs, cf);
+            sColX[i] = xc; sColS[i] = cs; sColF[i] = cf;
+        }
+        __syncthreads();
+    }
     auto stage = [&](int first, int cnt) {
         if constexpr (FIRST) {
-            constexpr int NQ = (WP + 31) / 32;
-            int xs[NQ], csx[NQ]; float cfx[NQ];
-#pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                xs[q] = clampi(x0 - M + lane + 32 * q, 0, w - 1);
-                csx[q] = 0; cfx[q] = 0.f;
-                if (coarse) resize_coef(xs[q], a.cw, a.sxs, csx[q], cfx[q]);
-            }
-            for (int r = wrp; r < cnt; r += NWARP) {
+            // item = one staged (row, column): the cnt * WP items of the step are dealt to the threads in order, so every
+            // round but the last has all lanes busy (a warp-per-row split leaves WP mod 32 lanes in its last round)
+            for (int idx = tid; idx < cnt * WP; idx += NTHR) {
+                const int r = idx / WP, rx = idx - r * WP;
                 const int y = clampi(y0 - M + first + r, 0, h - 1);
-                int csy = 0; float cfy = 0.f;
-                if (coarse) resize_coef(y, a.ch, a.sys, csy, cfy);
-#pragma unroll
-                for (int q = 0; q < NQ; q++) {
-                    const int rx = lane + 32 * q;
-                    if (rx < WP) {
-                        float2 fi = make_float2(0.f, 0.f);
-                        if (coarse) fi = upsample_flow_tab(coarse, a.cw, a.ch, csx[q], cfx[q], csy, cfy, a.fscale);
-                        float mm[5];
-                        update_matrices_core<false>(xs[q], y, fi.x, fi.y, w, h, R0, R1, a.pitch, mm);
-#pragma unroll
-                        for (int c = 0; c < 5; c++) sRaw[(c * RB + r) * WPA + D + rx] = mm[c];
-                    }
+                const int x = sColX[rx];
+                float2 fi = make_float2(0.f, 0.f);
+                if (coarse) {
+                    int csy; float cfy;
+                    resize_coef(y, a.ch, a.sys, csy, cfy);
+                    fi = upsample_flow_tab(coarse, a.cw, a.ch, sColS[rx], sColF[rx], csy, cfy, a.fscale);
                 }
+                float mm[5];
+                update_matrices_core<false>(x, y, fi.x, fi.y, w, h, R0, R1, a.pitch, mm);
+#pragma unroll
+                for (int c = 0; c < 5; c++) sRaw[(c * RB + r) * WPA + D + rx] = mm[c];
             }
         } else {
             const int ytop = y0 - M + first;
