@@ -790,8 +790,8 @@ def run_ours(args, rank, world, local_rank):
             for name, ref, (ww, hh, PP, BB, st_) in [
                     ("C2 Gaussian winsize 10 (the reference's live driver)", "main.cpp:1119,1481", (W, H, (0.5, 2, 10, 3, 15, 1.2, 256), int(os.environ.get("RC_BENCH_SEC_B", "64")), 8)),
                     ("C2 Gaussian winsize 20", "main.cpp:609,961", (W, H, (0.5, 2, 20, 3, 15, 1.2, 256), int(os.environ.get("RC_BENCH_SEC_B", "64")), 8)),
-                    ("C3 4K 5 layers winsize 21 box", "BASELINE configs[2]", (3840, 2160, (0.5, 4, 21, 3, 15, 1.2, 0), int(os.environ.get("RC_BENCH_SEC_B4K", "16")), 8)),
-                    ("C3 4K 5 layers winsize 21 Gaussian", "BASELINE configs[2]", (3840, 2160, (0.5, 4, 21, 3, 15, 1.2, 256), int(os.environ.get("RC_BENCH_SEC_B4K", "16")), 8))]:
+                    ("C3 4K 5 layers winsize 21 box", "BASELINE configs[2]", (3840, 2160, (0.5, 4, 21, 3, 15, 1.2, 0), int(os.environ.get("RC_BENCH_SEC_B4K", "32")), 8)),
+                    ("C3 4K 5 layers winsize 21 Gaussian", "BASELINE configs[2]", (3840, 2160, (0.5, 4, 21, 3, 15, 1.2, 256), int(os.environ.get("RC_BENCH_SEC_B4K", "32")), 8))]:
                 sec.append(guarded(measure_flow_config, name, torch, dev, stream, name, ref, ww, hh, PP, BB, st_, peak, sampler2))
             sec.append(guarded(measure_advection, "C4 advection", torch, dev, stream, 50, peak, sampler2))
             sec.append(guarded(measure_cpp_dropin, "C++ drop-in loop", frames))
