@@ -103,9 +103,10 @@ def test_legacy_frame_loop_end_to_end(oracle):
     loop.close()
 
 
-@pytest.mark.parametrize("W", [10, 3])
+@pytest.mark.parametrize("W", [10, 3, 100, 1])
 def test_window_mean(oracle, W):
-    """main.cpp:1143-1153: avg -= buf[i]/W; buf[i] = flow.clone(); avg += buf[i]/W; 2.5 windows of updates"""
+    """main.cpp:1143-1153 (W = 10), :1505-1515 (W = 100): avg -= buf[i]/W; buf[i] = flow.clone(); avg += buf[i]/W;
+    2.5 windows of updates (W = 1: the mean follows the latest flow)"""
     rng = np.random.default_rng(W)
     h, w = 33, 47
     win = R.Window(w, h, W)
